@@ -1,0 +1,168 @@
+"""flash_attention_metal_b200 -- host-side mirror of the reference's operator surface.
+
+The product is ``libflash_attn_b200.so`` (hand-written CUDA for sm_100a behind the
+C ABI in ``include/flash_attn_b200.h``).  This module is only its ctypes binding:
+one Python function per kernel of the reference, same name, same argument order
+as the reference's buffer indices (``main.mm`` dispatch sites are cited in the
+header).  Arguments are raw device pointers (``int``) or anything exposing
+``data_ptr()`` (a torch CUDA tensor); nothing is computed in Python and there is
+no CPU fallback -- if the shared library is missing the import fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libflash_attn_b200.so")
+
+FP16, BF16 = 0, 1
+NAIVE, V1, V2 = 0, 1, 2
+
+#: every symbol include/flash_attn_b200.h declares (tests check they are all exported)
+EXPORTS = (
+    "naive_attention", "flash_attention", "flash_attention_v2", "flash_attention_v2_batched",
+    "flash_attention_simd", "flash_attention_v4_half", "flash_attention_backward",
+    "fa_workspace_bytes_backward", "fa_host_attention_f32", "fa_host_attention_half",
+    "fa_last_error", "fa_version", "fa_device_count", "fa_launch_count", "fa_reset_launch_count",
+)
+
+
+class FlashAttnError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the library in-tree with nvcc for sm_100a (no GPU needed)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", _HERE, "-j8"], stdout=out)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FlashAttnError(
+                f"{LIB_PATH} is missing: build it with `make -C {_HERE}` or "
+                "`python -c 'import __graft_entry__ as g; g.build()'` -- there is no fallback path")
+        L = C.CDLL(LIB_PATH)
+        vp, i32, i64, f32, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t
+        for name in ("naive_attention", "flash_attention", "flash_attention_v2"):
+            getattr(L, name).argtypes = [vp, vp, vp, vp, i32, i32, f32, i32, vp]
+        L.flash_attention_v2_batched.argtypes = [vp, vp, vp, vp, i32, i32, f32, i64, i64, i32, i32, i32, vp]
+        L.flash_attention_simd.argtypes = [vp, vp, vp, vp, i32, i32, f32, i32, vp]
+        L.flash_attention_v4_half.argtypes = [vp, vp, vp, vp, i32, i32, f32, i64, i64, vp, i32, i32, i32, i32, vp]
+        L.flash_attention_backward.argtypes = [vp] * 9 + [i32, i32, f32, i64, i64, i32, i32, i32, i32, vp, sz, vp]
+        L.fa_workspace_bytes_backward.argtypes = [i32, i32, i32, i32]
+        L.fa_workspace_bytes_backward.restype = sz
+        L.fa_host_attention_f32.argtypes = [i32, vp, vp, vp, vp, i32, i32, f32, i32]
+        L.fa_host_attention_half.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, i32, i32]
+        L.fa_last_error.restype = C.c_char_p
+        L.fa_launch_count.restype = C.c_long
+        L.fa_reset_launch_count.restype = None
+        if hasattr(L, "fa_ring_create"):
+            L.fa_ring_unique_id_bytes.restype = i32
+            L.fa_ring_get_unique_id.argtypes = [vp, i32]
+            L.fa_ring_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32]
+            L.fa_ring_destroy.argtypes = [vp]
+            L.fa_ring_workspace_bytes.argtypes = [i32, i32, i32, i32]
+            L.fa_ring_workspace_bytes.restype = sz
+            L.fa_ring_attention_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, i32, vp, sz, vp]
+        _lib = L
+    return _lib
+
+
+def _ptr(x) -> int | None:
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    if hasattr(x, "ctypes"):  # numpy array: host pointer (fa_host_* calls only)
+        return x.ctypes.data
+    raise TypeError(f"cannot take a pointer from {type(x)!r}")
+
+
+def _stream(stream) -> int | None:
+    if stream is None:
+        return None
+    return getattr(stream, "cuda_stream", stream)
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise FlashAttnError(f"flash_attn_b200 error {rc}: {lib().fa_last_error().decode()}")
+
+
+# -- fp32 variants: (Q, K, V, O, N, D, scale) = reference buffer indices 0..6 --
+def naive_attention(Q, K, V, O, N, D, scale, is_causal=False, stream=None):
+    """kernels.metal:12-64 / main.mm:162-191."""
+    _check(lib().naive_attention(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), N, D, scale, int(is_causal), _stream(stream)))
+
+
+def flash_attention(Q, K, V, O, N, D, scale, is_causal=False, stream=None):
+    """V1, kernels.metal:72-171 / main.mm:198-224."""
+    _check(lib().flash_attention(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), N, D, scale, int(is_causal), _stream(stream)))
+
+
+def flash_attention_v2(Q, K, V, O, N, D, scale, is_causal=False, stream=None):
+    """V2, kernels.metal:462-596 / main.mm:259-275."""
+    _check(lib().flash_attention_v2(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), N, D, scale, int(is_causal), _stream(stream)))
+
+
+def flash_attention_v2_batched(Q, K, V, O, N, D, scale, batch_stride, head_stride, is_causal, B, H, stream=None):
+    _check(lib().flash_attention_v2_batched(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), N, D, scale, batch_stride,
+                                            head_stride, int(is_causal), B, H, _stream(stream)))
+
+
+# -- 16-bit variants -----------------------------------------------------------
+def flash_attention_simd(Q, K, V, O, N, D, scale, dtype=FP16, stream=None):
+    """V3, kernels.metal:177-455 / main.mm:332-349."""
+    _check(lib().flash_attention_simd(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), N, D, scale, dtype, _stream(stream)))
+
+
+def flash_attention_v4_half(Q, K, V, O, N, D, scale, batch_stride, head_stride, L_out, is_causal, B=1, H=1,
+                            dtype=FP16, stream=None):
+    """V4, kernels.metal:600-883 / main.mm:414-440 (buffer indices 0..10, then B, H, dtype)."""
+    _check(lib().flash_attention_v4_half(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), N, D, scale, batch_stride, head_stride,
+                                         _ptr(L_out), int(is_causal), B, H, dtype, _stream(stream)))
+
+
+def workspace_bytes_backward(N, D, B, H) -> int:
+    return int(lib().fa_workspace_bytes_backward(N, D, B, H))
+
+
+def flash_attention_backward(Q, K, V, O, dO, L, dQ, dK, dV, N, D, scale, batch_stride, head_stride, is_causal,
+                             B=1, H=1, dtype=FP16, workspace=None, workspace_bytes=0, stream=None):
+    """kernels.metal:905-1265 / main.mm:1027-1061 (buffer indices 0..14, then B, H, dtype, workspace)."""
+    _check(lib().flash_attention_backward(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(dO), _ptr(L), _ptr(dQ), _ptr(dK),
+                                          _ptr(dV), N, D, scale, batch_stride, head_stride, int(is_causal), B, H,
+                                          dtype, _ptr(workspace), workspace_bytes, _stream(stream)))
+
+
+# -- host-buffer calls (numpy arrays or host pointers) ---------------------------
+def host_attention_f32(variant, Q, K, V, O, N, D, scale, is_causal=False):
+    _check(lib().fa_host_attention_f32(variant, _ptr(Q), _ptr(K), _ptr(V), _ptr(O), N, D, scale, int(is_causal)))
+
+
+def host_attention_half(Q, K, V, O, L_out, N, D, scale, is_causal, B, H, dtype):
+    _check(lib().fa_host_attention_half(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(L_out), N, D, scale,
+                                        int(is_causal), B, H, dtype))
+
+
+def launch_count() -> int:
+    return int(lib().fa_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().fa_reset_launch_count()
+
+
+def version() -> int:
+    return int(lib().fa_version())

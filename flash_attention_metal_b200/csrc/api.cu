@@ -1,0 +1,149 @@
+// extern "C" entry points of libflash_attn_b200.so (see include/flash_attn_b200.h).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "fa_internal.h"
+
+namespace fa {
+
+static thread_local char g_err[512] = "";
+static thread_local long g_launches = 0;
+
+int set_error(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch(int n) { g_launches += n; }
+
+}  // namespace fa
+
+using namespace fa;
+
+extern "C" {
+
+const char *fa_last_error(void) { return g_err; }
+int fa_version(void) { return 100; }
+long fa_launch_count(void) { return g_launches; }
+void fa_reset_launch_count(void) { g_launches = 0; }
+
+int fa_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return n;
+}
+
+int naive_attention(const float *Q, const float *K, const float *V, float *O, int N, int D,
+                    float scale, int is_causal, fa_stream_t stream) {
+  return launch_fp32(0, Q, K, V, O, N, D, scale, 0, 0, is_causal, 1, 1, (cudaStream_t)stream);
+}
+
+int flash_attention(const float *Q, const float *K, const float *V, float *O, int N, int D,
+                    float scale, int is_causal, fa_stream_t stream) {
+  return launch_fp32(1, Q, K, V, O, N, D, scale, 0, 0, is_causal, 1, 1, (cudaStream_t)stream);
+}
+
+int flash_attention_v2(const float *Q, const float *K, const float *V, float *O, int N, int D,
+                       float scale, int is_causal, fa_stream_t stream) {
+  return launch_fp32(2, Q, K, V, O, N, D, scale, 0, 0, is_causal, 1, 1, (cudaStream_t)stream);
+}
+
+int flash_attention_v2_batched(const float *Q, const float *K, const float *V, float *O, int N,
+                               int D, float scale, int64_t batch_stride, int64_t head_stride,
+                               int is_causal, int B, int H, fa_stream_t stream) {
+  return launch_fp32(2, Q, K, V, O, N, D, scale, batch_stride, head_stride, is_causal, B, H,
+                     (cudaStream_t)stream);
+}
+
+int flash_attention_simd(const void *Q, const void *K, const void *V, void *O, int N, int D,
+                         float scale, int dtype, fa_stream_t stream) {
+  return launch_fwd_tc(Q, K, V, O, nullptr, N, D, scale, (int64_t)N * D, (int64_t)N * D, 0, 1, 1,
+                       dtype, (cudaStream_t)stream);
+}
+
+int flash_attention_v4_half(const void *Q, const void *K, const void *V, void *O, int N, int D,
+                            float scale, int64_t batch_stride, int64_t head_stride, float *L_out,
+                            int is_causal, int B, int H, int dtype, fa_stream_t stream) {
+  return launch_fwd_tc(Q, K, V, O, L_out, N, D, scale, batch_stride, head_stride, is_causal, B, H,
+                       dtype, (cudaStream_t)stream);
+}
+
+int flash_attention_backward(const void *Q, const void *K, const void *V, const void *O,
+                             const void *dO, const float *L, float *dQ, float *dK, float *dV,
+                             int N, int D, float scale, int64_t batch_stride,
+                             int64_t head_stride, int is_causal, int B, int H, int dtype,
+                             void *workspace, size_t workspace_bytes, fa_stream_t stream) {
+  return launch_bwd_tc(Q, K, V, O, dO, L, dQ, dK, dV, N, D, scale, batch_stride, head_stride,
+                       is_causal, B, H, dtype, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+size_t fa_workspace_bytes_backward(int N, int D, int B, int H) {
+  (void)D;
+  if (N < 1 || B < 1 || H < 1) return 0;
+  // D_i = rowsum(dO o O): one float per (b, h, i), rounded up to 256 bytes
+  size_t bytes = (size_t)B * H * N * sizeof(float);
+  return (bytes + 255) & ~(size_t)255;
+}
+
+// ---- host-buffer entry points ------------------------------------------------
+namespace {
+struct DevBuf {
+  void *p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n); }
+};
+}  // namespace
+
+int fa_host_attention_f32(int variant, const float *Q, const float *K, const float *V, float *O,
+                          int N, int D, float scale, int is_causal) {
+  FA_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0, 1 or 2");
+  FA_REQUIRE(Q && K && V && O && N >= 1 && D >= 1, "bad arguments");
+  const size_t bytes = (size_t)N * D * sizeof(float);
+  DevBuf q, k, v, o;
+  FA_CUDA_CHECK(q.alloc(bytes));
+  FA_CUDA_CHECK(k.alloc(bytes));
+  FA_CUDA_CHECK(v.alloc(bytes));
+  FA_CUDA_CHECK(o.alloc(bytes));
+  FA_CUDA_CHECK(cudaMemcpyAsync(q.p, Q, bytes, cudaMemcpyHostToDevice, 0));
+  FA_CUDA_CHECK(cudaMemcpyAsync(k.p, K, bytes, cudaMemcpyHostToDevice, 0));
+  FA_CUDA_CHECK(cudaMemcpyAsync(v.p, V, bytes, cudaMemcpyHostToDevice, 0));
+  int rc = launch_fp32(variant, (const float *)q.p, (const float *)k.p, (const float *)v.p,
+                       (float *)o.p, N, D, scale, 0, 0, is_causal, 1, 1, 0);
+  if (rc != FA_OK) return rc;
+  FA_CUDA_CHECK(cudaMemcpyAsync(O, o.p, bytes, cudaMemcpyDeviceToHost, 0));
+  FA_CUDA_CHECK(cudaStreamSynchronize(0));
+  return FA_OK;
+}
+
+int fa_host_attention_half(const void *Q, const void *K, const void *V, void *O, float *L_out,
+                           int N, int D, float scale, int is_causal, int B, int H, int dtype) {
+  FA_REQUIRE(Q && K && V && O && N >= 1 && D >= 1 && B >= 1 && H >= 1, "bad arguments");
+  const size_t bytes = (size_t)B * H * N * D * 2;
+  const size_t lbytes = (size_t)B * H * N * sizeof(float);
+  DevBuf q, k, v, o, l;
+  FA_CUDA_CHECK(q.alloc(bytes));
+  FA_CUDA_CHECK(k.alloc(bytes));
+  FA_CUDA_CHECK(v.alloc(bytes));
+  FA_CUDA_CHECK(o.alloc(bytes));
+  if (L_out) FA_CUDA_CHECK(l.alloc(lbytes));
+  FA_CUDA_CHECK(cudaMemcpyAsync(q.p, Q, bytes, cudaMemcpyHostToDevice, 0));
+  FA_CUDA_CHECK(cudaMemcpyAsync(k.p, K, bytes, cudaMemcpyHostToDevice, 0));
+  FA_CUDA_CHECK(cudaMemcpyAsync(v.p, V, bytes, cudaMemcpyHostToDevice, 0));
+  int rc = launch_fwd_tc(q.p, k.p, v.p, o.p, (float *)l.p, N, D, scale, (int64_t)H * N * D,
+                         (int64_t)N * D, is_causal, B, H, dtype, 0);
+  if (rc != FA_OK) return rc;
+  FA_CUDA_CHECK(cudaMemcpyAsync(O, o.p, bytes, cudaMemcpyDeviceToHost, 0));
+  if (L_out) FA_CUDA_CHECK(cudaMemcpyAsync(L_out, l.p, lbytes, cudaMemcpyDeviceToHost, 0));
+  FA_CUDA_CHECK(cudaStreamSynchronize(0));
+  return FA_OK;
+}
+
+}  // extern "C"

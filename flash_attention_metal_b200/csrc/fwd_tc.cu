@@ -1,0 +1,400 @@
+// 16-bit FlashAttention forward for sm_100a: tcgen05 MMAs with TMEM accumulators,
+// TMA-fed mbarrier pipeline, warp-specialised roles.
+//
+// Replaces flash_attention_v4_half_kernel (kernels.metal:600-883) and, called with
+// B = H = 1 / L = NULL / causal = 0, flash_attention_simd_kernel (kernels.metal:177-455).
+//
+// One CTA per SM works on 256 query rows of one (batch, head): two 128-row Q tiles
+// that share every K/V tile brought in by TMA (halves L2->SM traffic) and ping-pong
+// on the tensor core so the softmax of one tile overlaps the MMAs of the other.
+//
+//   warps 0-3   softmax, Q tile 0   one thread per query row (TMEM lane = row):
+//   warps 4-7   softmax, Q tile 1   tcgen05.ld S -> mask -> online softmax (exp2,
+//                                   conditional rescale) -> tcgen05.st P (16-bit)
+//                                   over S; epilogue O / l -> global, L
+//   warp  8     MMA issuer          one elected thread: S_t = Q_t K_j^T (smem x smem),
+//                                   O_t += P_t V_j (TMEM x smem), tcgen05.commit -> mbarriers
+//   warp  9     TMA producer        one elected thread: Q tiles once, then K_j, V_j into a
+//                                   ring of shared-memory stages
+//   warps 10-11 idle (complete the warpgroup for setmaxnreg)
+//
+// TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D);
+// P_t aliases the first 64 columns of S_t (two 16-bit values per column).
+//
+// Shared memory tiles are [128 rows][64 elements] boxes (128-byte rows, 128-byte
+// swizzle) exactly as TMA writes them: K-major operands for Q K^T (Q and K rows are
+// the M/N index, head dim is K), MN-major B operand for P V (V rows are the K index).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "fa_internal.h"
+#include "sm100_ptx.cuh"
+#include "tensormap.h"
+
+namespace fa {
+namespace {
+
+using namespace ptx;
+
+constexpr int kBM = 128;          // query rows per tile (= TMEM lanes)
+constexpr int kBN = 128;          // keys per tile
+constexpr int kThreads = 384;
+constexpr int kMmaWarp = 8;
+constexpr int kLoadWarp = 9;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+constexpr float kRescaleThreshold = 8.0f;  // in log2 units: P may grow to 2^8 before O is rescaled
+
+template <int D>
+struct FwdCfg {
+  static constexpr int kChunks = D / 64;                    // 64-element (128 B) column chunks
+  static constexpr int kChunkBytes = 128 * 128;             // 128 rows x 128 B
+  static constexpr int kTileBytes = kChunks * kChunkBytes;  // one Q, K or V tile
+  static constexpr int kStages = D == 128 ? 4 : 8;
+  static constexpr int kSmemTiles = (2 + kStages) * kTileBytes;
+  static constexpr int kSmemBytes = kSmemTiles + 1024 /*alignment slack*/ + 256 /*barriers*/;
+};
+
+struct FwdParams {
+  void *O;
+  float *L;
+  int N;
+  int H;
+  float scale;        // multiplies the dot product
+  float scale_log2;   // scale * log2(e)
+  int64_t batch_stride, head_stride;  // elements
+  int causal;
+};
+
+template <int D, int IS_BF16>
+__global__ void __launch_bounds__(kThreads, 1)
+fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+              const __grid_constant__ CUtensorMap tmV, const FwdParams p) {
+  using Cfg = FwdCfg<D>;
+  extern __shared__ unsigned char smem_raw[];
+  // 128-byte swizzle atoms are 1024 B: align the tile area
+  unsigned char *smem = reinterpret_cast<unsigned char *>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  unsigned char *sQ = smem;                           // 2 tiles
+  unsigned char *sKV = smem + 2 * Cfg::kTileBytes;    // kStages tiles
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemTiles);
+  uint64_t *q_full = bars;                       // [2]
+  uint64_t *s_full = bars + 2;                   // [2]
+  uint64_t *p_full = bars + 4;                   // [2]
+  uint64_t *o_full = bars + 6;                   // [2]
+  uint64_t *kv_full = bars + 8;                  // [kStages]
+  uint64_t *kv_empty = bars + 8 + Cfg::kStages;  // [kStages]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8 + 2 * Cfg::kStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int h = blockIdx.y, b = blockIdx.z;
+  // causal: the last row blocks have the most keys -> schedule them first
+  const int qb = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int q_row0 = qb * 2 * kBM;
+  const int n_kv_all = (p.N + kBN - 1) / kBN;
+  // KV tiles each Q tile needs (0 = tile entirely past N)
+  int n_t[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) {
+    const int r0 = q_row0 + t * kBM;
+    n_t[t] = r0 >= p.N ? 0 : (p.causal ? min(n_kv_all, r0 / kBN + 1) : n_kv_all);
+  }
+  const int nmax = max(n_t[0], n_t[1]);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], kBM);
+      mbar_init(&o_full[i], 1);
+    }
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // =========================== softmax warpgroups ===========================
+    setmaxnreg_inc<216>();
+    const int t = warp >> 2;
+    const int row_in_tile = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + t * kBN;
+    const uint32_t tO = tmem_base + lane_off + 256 + t * D;
+    const int grow = q_row0 + t * kBM + row_in_tile;
+    const int nt = n_t[t];
+    float m_run = -CUDART_INF_F;  // reference max (raw score units) the accumulators are relative to
+    float l_run = 0.f;
+
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      uint32_t s[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
+      tmem_wait_ld();
+
+      // ---- masks: causal diagonal tile (always the last one) / keys past N ----
+      const bool diag = p.causal && (j == nt - 1);
+      const bool tail = (j + 1) * kBN > p.N;
+      if (diag || tail) {
+        int limit = p.N - 1 - j * kBN;                 // last valid key column in this tile
+        if (diag) limit = min(limit, grow - j * kBN);  // key <= query row
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i > limit) s[c][i] = 0xff800000u;  // -inf
+      }
+      // ---- row max ------------------------------------------------------------
+      float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[c][i]));
+      const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      // ---- conditional rescale: only move the reference max when it grows by more
+      //      than 2^threshold; below that P <= 2^threshold, safe in fp32 sums and 16-bit P
+      float acc_scale = 1.f;
+      if (j == 0) {
+        m_run = m_tile;
+      } else {
+        const float grow_log2 = (m_tile - m_run) * p.scale_log2;
+        if (grow_log2 > kRescaleThreshold) {
+          acc_scale = ex2(-grow_log2);
+          m_run = m_tile;
+        }
+      }
+      if (j > 0 && __any_sync(0xffffffffu, acc_scale != 1.f)) {
+        // PV_t(j-1) completed before S_t(j) (in-order tensor pipe), PV_t(j) waits for
+        // p_full below: O_t is quiescent here.
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tO + c * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * acc_scale);
+          tmem_st32(tO + c * 32, o);
+        }
+      }
+      // ---- P = exp2(s * scale_log2 - m * scale_log2), row sum, pack ---------------
+      const float neg_m = -m_run * p.scale_log2;
+      float sum[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[2][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2(fmaf(__uint_as_float(s[c][i]), p.scale_log2, neg_m));
+          const float p1 = ex2(fmaf(__uint_as_float(s[c][i + 1]), p.scale_log2, neg_m));
+          sum[(i >> 1) & 3] += p0 + p1;
+          pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack2<IS_BF16>(p0, p1);
+        }
+      l_run = l_run * acc_scale + ((sum[0] + sum[1]) + (sum[2] + sum[3]));
+      tmem_st32(tS, pk[0]);
+      tmem_st32(tS + 32, pk[1]);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[t]);
+    }
+
+    if (nt > 0) {
+      // ------------------------------ epilogue -------------------------------
+      mbar_wait(&o_full[t], 0);
+      tc_fence_after();
+      const float inv_l = 1.f / l_run;
+      const int64_t head_off = (int64_t)b * p.batch_stride + (int64_t)h * p.head_stride;
+      uint16_t *orow = reinterpret_cast<uint16_t *>(p.O) + head_off + (int64_t)grow * D;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tmem_wait_ld();
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          w[i] = pack2<IS_BF16>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+        if (grow < p.N) {
+          uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+        }
+      }
+      if (p.L != nullptr && grow < p.N)
+        p.L[head_off / D + grow] = m_run * p.scale + lg2(l_run) * kLn2;
+    }
+  } else {
+    setmaxnreg_dec<64>();
+    if (warp == kLoadWarp) {
+      // ============================== TMA producer ==============================
+      if (elect_one()) {
+        prefetch_tensormap(&tmQ);
+        prefetch_tensormap(&tmK);
+        prefetch_tensormap(&tmV);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+          if (n_t[t] > 0) {
+            mbar_arrive_expect_tx(&q_full[t], Cfg::kTileBytes);
+#pragma unroll
+            for (int c = 0; c < Cfg::kChunks; ++c)
+              tma_load_4d(sQ + t * Cfg::kTileBytes + c * Cfg::kChunkBytes, &tmQ, &q_full[t], c * 64,
+                          q_row0 + t * kBM, h, b);
+          }
+        for (int item = 0; item < 2 * nmax; ++item) {
+          const int stage = item % Cfg::kStages;
+          const int round = item / Cfg::kStages;
+          mbar_wait(&kv_empty[stage], (round & 1) ^ 1);
+          mbar_arrive_expect_tx(&kv_full[stage], Cfg::kTileBytes);
+          const CUtensorMap *map = (item & 1) ? &tmV : &tmK;
+#pragma unroll
+          for (int c = 0; c < Cfg::kChunks; ++c)
+            tma_load_4d(sKV + stage * Cfg::kTileBytes + c * Cfg::kChunkBytes, map, &kv_full[stage],
+                        c * 64, (item >> 1) * kBN, h, b);
+        }
+      }
+      __syncwarp();
+    } else if (warp == kMmaWarp) {
+      // =============================== MMA issuer ===============================
+      if (elect_one()) {
+        constexpr uint32_t idesc_qk = make_idesc(kBM, kBN, IS_BF16, 0, 0);
+        constexpr uint32_t idesc_pv = make_idesc(kBM, D, IS_BF16, 0, 1);
+        const uint32_t sQ_addr = smem_u32(sQ);
+        const uint32_t sKV_addr = smem_u32(sKV);
+        auto wait_full = [&](int item) -> uint32_t {
+          const int stage = item % Cfg::kStages;
+          mbar_wait(&kv_full[stage], (item / Cfg::kStages) & 1);
+          tc_fence_after();
+          return (uint32_t)stage;
+        };
+        auto issue_qk = [&](int t, uint32_t kstage) {
+          const uint32_t qa = sQ_addr + t * Cfg::kTileBytes;
+          const uint32_t ka = sKV_addr + kstage * Cfg::kTileBytes;
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk) {
+            const uint32_t off = (kk >> 2) * Cfg::kChunkBytes + (kk & 3) * 32;
+            mma_ss(tmem_base + t * kBN, make_sdesc_sw128(qa + off, 16, 1024),
+                   make_sdesc_sw128(ka + off, 16, 1024), idesc_qk, kk > 0);
+          }
+        };
+        auto issue_pv = [&](int t, uint32_t vstage, bool accumulate) {
+          const uint32_t va = sKV_addr + vstage * Cfg::kTileBytes;
+#pragma unroll
+          for (int kk = 0; kk < kBN / 16; ++kk)
+            mma_ts(tmem_base + 256 + t * D, tmem_base + t * kBN + kk * 8,
+                   make_sdesc_sw128(va + kk * 2048, Cfg::kChunkBytes, 1024), idesc_pv,
+                   (accumulate || kk > 0) ? 1u : 0u);
+        };
+
+        const uint32_t ks0 = wait_full(0);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+          if (n_t[t] > 0) {
+            mbar_wait(&q_full[t], 0);
+            tc_fence_after();
+            issue_qk(t, ks0);
+            tc_commit(&s_full[t]);
+          }
+        tc_commit(&kv_empty[ks0]);
+        for (int j = 0; j < nmax; ++j) {
+          const uint32_t vs = wait_full(2 * j + 1);
+          const bool more = j + 1 < nmax;
+          const uint32_t ks = more ? wait_full(2 * j + 2) : 0u;
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            if (j < n_t[t]) {
+              mbar_wait(&p_full[t], j & 1);
+              tc_fence_after();
+              issue_pv(t, vs, j > 0);
+              if (j == n_t[t] - 1) tc_commit(&o_full[t]);
+            }
+            if (j + 1 < n_t[t]) {
+              issue_qk(t, ks);
+              tc_commit(&s_full[t]);
+            }
+          }
+          tc_commit(&kv_empty[vs]);
+          if (more) tc_commit(&kv_empty[ks]);
+        }
+      }
+      __syncwarp();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int D, int IS_BF16>
+int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUtensorMap &tmV,
+                       const FwdParams &p, int B, cudaStream_t stream) {
+  using Cfg = FwdCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    FA_CUDA_CHECK(cudaFuncSetAttribute(fwd_tc_kernel<D, IS_BF16>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid((p.N + 2 * kBM - 1) / (2 * kBM), p.H, B);
+  fwd_tc_kernel<D, IS_BF16><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  FA_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return FA_OK;
+}
+
+}  // namespace
+
+int launch_fwd_tc(const void *Q, const void *K, const void *V, void *O, float *L, int N, int D,
+                  float scale, int64_t batch_stride, int64_t head_stride, int is_causal, int B, int H,
+                  int dtype, cudaStream_t stream) {
+  FA_REQUIRE(Q && K && V && O, "null tensor pointer");
+  FA_REQUIRE(N >= 1, "N must be >= 1 (got %d)", N);
+  FA_REQUIRE(D == 64 || D == 128, "D must be 64 or 128 (got %d)", D);
+  FA_REQUIRE(B >= 1 && H >= 1 && H <= 65535 && B <= 65535, "bad B/H (%d, %d)", B, H);
+  FA_REQUIRE(dtype == FA_DTYPE_FP16 || dtype == FA_DTYPE_BF16, "dtype must be FA_DTYPE_FP16 or FA_DTYPE_BF16");
+  FA_REQUIRE(scale > 0.f, "scale must be positive");
+  FA_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O), "Q/K/V/O must be 16-byte aligned");
+  FA_REQUIRE(batch_stride % 8 == 0 && head_stride % 8 == 0, "strides must be multiples of 8 elements");
+  FA_REQUIRE((H == 1 || head_stride >= (int64_t)N * D) && (B == 1 || batch_stride >= (int64_t)N * D),
+             "heads overlap: stride smaller than N*D");
+  FA_REQUIRE(L == nullptr || (head_stride % D == 0 && batch_stride % D == 0),
+             "L_out needs strides that are multiples of D (L index = offset / D, kernels.metal:623)");
+  CUtensorMap tmQ, tmK, tmV;
+  int rc;
+  if ((rc = make_tensor_map_bhnd(&tmQ, Q, dtype, N, D, H, B, head_stride, batch_stride, kBM)) != FA_OK) return rc;
+  if ((rc = make_tensor_map_bhnd(&tmK, K, dtype, N, D, H, B, head_stride, batch_stride, kBN)) != FA_OK) return rc;
+  if ((rc = make_tensor_map_bhnd(&tmV, V, dtype, N, D, H, B, head_stride, batch_stride, kBN)) != FA_OK) return rc;
+  FwdParams p;
+  p.O = O;
+  p.L = L;
+  p.N = N;
+  p.H = H;
+  p.scale = scale;
+  p.scale_log2 = scale * kLog2e;
+  p.batch_stride = batch_stride;
+  p.head_stride = head_stride;
+  p.causal = is_causal ? 1 : 0;
+  if (D == 64)
+    return dtype == FA_DTYPE_BF16 ? launch_fwd_tc_impl<64, 1>(tmQ, tmK, tmV, p, B, stream)
+                                  : launch_fwd_tc_impl<64, 0>(tmQ, tmK, tmV, p, B, stream);
+  return dtype == FA_DTYPE_BF16 ? launch_fwd_tc_impl<128, 1>(tmQ, tmK, tmV, p, B, stream)
+                                : launch_fwd_tc_impl<128, 0>(tmQ, tmK, tmV, p, B, stream);
+}
+
+}  // namespace fa

@@ -1,0 +1,55 @@
+// Host-side TMA descriptor construction.  cuTensorMapEncodeTiled lives in the
+// driver (libcuda); it is resolved at run time through the CUDA runtime so the
+// library has no link-time dependency on libcuda and can be loaded (not run) on a
+// machine without a driver.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fa_internal.h"
+
+namespace fa {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *,
+                                  const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// Row-major [B, H, N, D] 16-bit tensor with element strides (batch_stride,
+// head_stride, D, 1); box = 64 elements (128 bytes) x box_rows rows, 128-byte
+// swizzle -- the layout the UMMA shared-memory descriptors in the kernels expect.
+inline int make_tensor_map_bhnd(CUtensorMap *map, const void *base, int dtype, int N, int D, int H,
+                                int B, int64_t head_stride, int64_t batch_stride, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return set_error(FA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+  // strides of dims 1..3 in bytes; a size-1 dim still needs a legal (multiple of 16) stride
+  cuuint64_t hs = (cuuint64_t)(H > 1 ? head_stride : (int64_t)N * D) * 2;
+  cuuint64_t bs = (cuuint64_t)(B > 1 ? batch_stride : (int64_t)H * N * D) * 2;
+  cuuint64_t strides[3] = {(cuuint64_t)D * 2, hs, bs};
+  cuuint32_t box[4] = {64u, (cuuint32_t)box_rows, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(map, dtype == FA_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                   4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(FA_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d; N=%d D=%d H=%d B=%d hs=%lld bs=%lld)",
+                     (int)r, N, D, H, B, (long long)head_stride, (long long)batch_stride);
+  return FA_OK;
+}
+
+}  // namespace fa

@@ -1,0 +1,137 @@
+/*
+ * flash_attn_b200.h -- C ABI of libflash_attn_b200.so (NVIDIA B200, sm_100a).
+ *
+ * The reference (2thleZ/flash_attention_metal) has no library API: its operator
+ * surface is the Metal dispatch convention of main.mm -- a kernel is chosen by
+ * its *string name*, its arguments are bound by *buffer index*, and the caller
+ * picks the grid.  Every entry point below replaces one such dispatch site and
+ * keeps the kernel's name and its argument order (buffer index order).  Paths
+ * are relative to the reference root.
+ *
+ * Common conventions:
+ *   - tensors are dense row-major [N, D] per head, D contiguous; batched calls
+ *     address head (b, h) at element offset b*batch_stride + h*head_stride
+ *     (kernels.metal:622, 932); L is contiguous [B, H, N] (kernels.metal:623).
+ *   - `scale` multiplies the dot product (kernels.metal:40, 146, 563, 763).
+ *   - causal: key j is excluded for query i when j > i (kernels.metal:748).
+ *   - all data pointers are DEVICE pointers, caller-owned, 16-byte aligned; the
+ *     library allocates nothing and keeps no state between calls.
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL =
+ *     the default stream) and return 0 on success or a negative FA_ERR_* code;
+ *     fa_last_error() gives the message (thread-local).  The reference exits the
+ *     process on error (main.mm:16-22); a library must not.
+ *   - differences from the reference, all additive: `is_causal` on the fp32
+ *     variants (the reference's fp32 kernels have none, kernels.metal:13-20);
+ *     explicit B and H (Metal's grid carried them, main.mm:848, 1001); 64-bit
+ *     strides (kernels.metal:608-609 uses int, which overflows at N = 1M);
+ *     D in {64, 128} (reference: 64 only, main.mm:12); dtype = fp16 or bf16
+ *     (reference: fp16 only).
+ *
+ * This header is plain C: no CUDA types appear in it.
+ */
+#ifndef FLASH_ATTN_B200_H_
+#define FLASH_ATTN_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *fa_stream_t; /* cudaStream_t */
+
+enum { FA_DTYPE_FP16 = 0, FA_DTYPE_BF16 = 1 };
+
+enum {
+  FA_OK = 0,
+  FA_ERR_INVALID = -1,    /* bad argument (shape, alignment, dtype, null pointer) */
+  FA_ERR_CUDA = -2,       /* a CUDA runtime/driver call failed */
+  FA_ERR_WORKSPACE = -3,  /* workspace missing or too small */
+  FA_ERR_UNSUPPORTED = -4,/* valid request the library does not implement */
+  FA_ERR_NCCL = -5        /* an NCCL call failed */
+};
+
+/* ---- fp32 variants: single head, Q/K/V/O float [N, D] ----------------------
+ * Buffer indices 0..6 of the reference = Q, K, V, O, N, D, scale.            */
+
+/* replaces naive_attention_kernel, kernels.metal:12-64, dispatched at
+ * main.mm:162-191 and 678-694.  One thread per query row, two passes over the
+ * keys, no shared memory: kept deliberately naive, it is the denominator of
+ * the speed-up columns in benchmark_results.csv. */
+int naive_attention(const float *Q, const float *K, const float *V, float *O, int N, int D,
+                    float scale, int is_causal, fa_stream_t stream);
+
+/* replaces flash_attention_kernel (V1, tiled), kernels.metal:72-171, dispatched
+ * at main.mm:198-224 and 708-724. */
+int flash_attention(const float *Q, const float *K, const float *V, float *O, int N, int D,
+                    float scale, int is_causal, fa_stream_t stream);
+
+/* replaces flash_attention_v2_kernel (V2, float4 + double buffering),
+ * kernels.metal:462-596, dispatched at main.mm:259-275 and 738-754. */
+int flash_attention_v2(const float *Q, const float *K, const float *V, float *O, int N, int D,
+                       float scale, int is_causal, fa_stream_t stream);
+
+/* Batched form of flash_attention_v2 (the
+ * reference's "high occupancy" table has a FlashV2 column it never fills,
+ * main.mm:883, 1202).  Heads addressed as in the 16-bit kernels. */
+int flash_attention_v2_batched(const float *Q, const float *K, const float *V, float *O, int N,
+                               int D, float scale, int64_t batch_stride, int64_t head_stride,
+                               int is_causal, int B, int H, fa_stream_t stream);
+
+/* ---- 16-bit variants (tensor cores: tcgen05 + TMEM + TMA) ------------------ */
+
+/* replaces flash_attention_simd_kernel (V3), kernels.metal:177-455, dispatched
+ * at main.mm:332-349 and 777-796: single head, no L, no causal mask. */
+int flash_attention_simd(const void *Q, const void *K, const void *V, void *O, int N, int D,
+                         float scale, int dtype, fa_stream_t stream);
+
+/* replaces flash_attention_v4_half_kernel (V4), kernels.metal:600-883,
+ * dispatched at main.mm:414-440, 520-546, 819-855, 977-1008.  Buffer indices
+ * 0..10 = Q, K, V, O, N, D, scale, batch_stride, head_stride, L_out, is_causal.
+ * L_out[b, h, i] = max_j(s_ij) + log(sum_j exp(s_ij - max)) over the scaled
+ * scores, natural log (kernels.metal:863); may be NULL. */
+int flash_attention_v4_half(const void *Q, const void *K, const void *V, void *O, int N, int D,
+                            float scale, int64_t batch_stride, int64_t head_stride, float *L_out,
+                            int is_causal, int B, int H, int dtype, fa_stream_t stream);
+
+/* replaces flash_attention_backward_kernel, kernels.metal:905-1265, dispatched
+ * at main.mm:1027-1061.  Buffer indices 0..14 = Q, K, V, O, dO (16-bit), L
+ * (float), dQ, dK, dV (float), N, D, scale, batch_stride, head_stride,
+ * is_causal.  All three gradients are fully overwritten (the reference needs
+ * dK/dV pre-zeroed because it accumulates them with float atomics,
+ * kernels.metal:1227, 1243; this library uses none and is run-to-run
+ * deterministic).  `workspace` holds D_i = sum_d O*dO (kernels.metal:983-990);
+ * size it with fa_workspace_bytes_backward(). */
+int flash_attention_backward(const void *Q, const void *K, const void *V, const void *O,
+                             const void *dO, const float *L, float *dQ, float *dK, float *dV,
+                             int N, int D, float scale, int64_t batch_stride,
+                             int64_t head_stride, int is_causal, int B, int H, int dtype,
+                             void *workspace, size_t workspace_bytes, fa_stream_t stream);
+
+size_t fa_workspace_bytes_backward(int N, int D, int B, int H);
+
+/* ---- host-buffer entry points ----------------------------------------------
+ * The reference's buffers are MTLResourceStorageModeShared (main.mm:104-115):
+ * the host writes inputs and reads outputs in place.  These calls give a
+ * caller with HOST tensors the same one-call behaviour: copy in, run, copy out,
+ * synchronise.  Contiguous [B, H, N, D].  They allocate device memory
+ * internally per call and are meant for the harness and for end-to-end timing. */
+int fa_host_attention_f32(int variant /*0 naive, 1 v1, 2 v2*/, const float *Q, const float *K,
+                          const float *V, float *O, int N, int D, float scale, int is_causal);
+int fa_host_attention_half(const void *Q, const void *K, const void *V, void *O, float *L_out,
+                           int N, int D, float scale, int is_causal, int B, int H, int dtype);
+
+/* ---- support ----------------------------------------------------------------*/
+const char *fa_last_error(void);
+int fa_version(void);          /* major*10000 + minor*100 + patch */
+int fa_device_count(void);     /* CUDA devices visible; <0 on error */
+/* Kernels launched by this library on the calling thread since the last reset
+ * (bench.py reports it as gpu_launches). */
+long fa_launch_count(void);
+void fa_reset_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLASH_ATTN_B200_H_ */
