@@ -1,0 +1,168 @@
+"""GPU parity tests for flash_attention_backward (C ABI) against the oracle's backward
+(main.mm:1091-1179 formulas, fp16/bf16 decoded correctly).  Bars: max-abs <= 2e-2
+(BASELINE.json, 16-bit) and, because gradients are small numbers, also <= 1 % (bf16) /
+0.2 % (fp16) of the largest reference gradient.  Gradients must be bit-identical from
+run to run (no float atomics, unlike kernels.metal:1227, 1243)."""
+import numpy as np
+import pytest
+
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+TOL_ABS = 2e-2
+TOL_REL = {oracle.FP16: 2e-3, oracle.BF16: 1e-2}
+
+
+@pytest.fixture(scope="module")
+def fa():
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import flash_attention_metal_b200 as fa
+
+    fa.lib()
+    return fa
+
+
+def dev(x):
+    import torch
+
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def run_backward(fa, bits, n, d, scale, causal, dtype, B=1, H=1):
+    import torch
+
+    qb, kb, vb, dob = bits
+    Q, K, V, dO = (dev(t.view(np.int16)) for t in (qb, kb, vb, dob))
+    shape = (B, H, n, d)
+    O = torch.zeros(shape, dtype=torch.int16, device="cuda")
+    L = torch.zeros((B, H, n), device="cuda")
+    hs, bs = n * d, H * n * d
+    fa.flash_attention_v4_half(Q, K, V, O, n, d, scale, bs, hs, L, causal, B, H, dtype)
+    grads = [torch.full(shape, float("nan"), device="cuda") for _ in range(3)]
+    wsb = fa.workspace_bytes_backward(n, d, B, H)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    fa.flash_attention_backward(Q, K, V, O, dO, L, *grads, n, d, scale, bs, hs, causal, B, H, dtype, ws, wsb)
+    torch.cuda.synchronize()
+    return [g.cpu().numpy() for g in grads]
+
+
+def make_bits(n, d, dtype, heads=(), seeds=(1, 2, 3, 4), mul=1.0):
+    size = int(np.prod(heads, dtype=np.int64)) * n * d if heads else n * d
+    return [oracle.to_half_bits(oracle.init_random(size, s).reshape(*heads, n, d) * np.float32(mul), dtype) for s in seeds]
+
+
+def check(got, want, dtype):
+    for g, w, name in zip(got, want, ("dQ", "dK", "dV")):
+        assert np.isfinite(g).all(), name
+        err = np.abs(g - w).max()
+        assert err <= TOL_ABS, (name, err)
+        assert err <= TOL_REL[dtype] * np.abs(w).max(), (name, err, np.abs(w).max())
+
+
+@pytest.mark.parametrize("dtype", [oracle.FP16, oracle.BF16])
+@pytest.mark.parametrize("causal", [False, True])
+@pytest.mark.parametrize("n,d", [(128, 64), (64, 64), (1, 64), (100, 64), (257, 64), (1024, 64),
+                                 (128, 128), (200, 128), (640, 128), (1024, 128)])
+def test_backward_matches_oracle(fa, dtype, causal, n, d):
+    scale = float(1.0 / np.sqrt(d))
+    bits = make_bits(n, d, dtype)
+    f = [oracle.from_half_bits(t, dtype) for t in bits]
+    want = oracle.backward(*f, scale, causal)
+    got = run_backward(fa, bits, n, d, scale, causal, dtype)
+    check([g[0, 0] for g in got], want, dtype)
+
+
+def test_backward_reference_harness_inputs(fa, golden):
+    """The reference's own backward check (main.mm:946-967, 1087-1195): N=128, D=64, fp16,
+    Q = K = V = dO = 0.01 * initRandom.  Compared with the frozen output of the reference's CPU
+    loops (decoded correctly); the bar is relative because the signal is ~1e-7."""
+    n, d = 128, 64
+    qb = golden["bwd128_qbits"]
+    got = run_backward(fa, (qb, qb, qb, qb), n, d, 0.125, False, oracle.FP16)
+    for g, key in zip(got, ("bwd128_dq", "bwd128_dk", "bwd128_dv")):
+        w = golden[key]
+        assert np.abs(g[0, 0] - w).max() <= 5e-3 * np.abs(w).max() + 1e-12, key
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_backward_batched_strided(fa, causal):
+    B, H, n, d = 2, 3, 300, 64
+    dtype = oracle.BF16
+    bits = make_bits(n, d, dtype, heads=(B, H), seeds=(5, 6, 7, 8))
+    f = [oracle.from_half_bits(t, dtype) for t in bits]
+    got = run_backward(fa, bits, n, d, 0.125, causal, dtype, B, H)
+    for b in range(B):
+        for h in range(H):
+            want = oracle.backward(*(t[b, h] for t in f), 0.125, causal)
+            check([g[b, h] for g in got], want, dtype)
+
+
+def test_backward_is_deterministic(fa):
+    n, d, dtype = 1024, 128, oracle.BF16
+    bits = make_bits(n, d, dtype, heads=(1, 4))
+    a = run_backward(fa, bits, n, d, 0.0884, True, dtype, 1, 4)
+    b = run_backward(fa, bits, n, d, 0.0884, True, dtype, 1, 4)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_backward_causal_structure(fa):
+    """Causal: dK/dV of the last key depend on the last query only; dQ of row 0 sees key 0 only,
+    where P = 1 and dS = P (dP - D) = 0 exactly."""
+    n, d, dtype = 384, 64, oracle.BF16
+    bits = make_bits(n, d, dtype)
+    dq, dk, dv = (g[0, 0] for g in run_backward(fa, bits, n, d, 0.125, True, dtype))
+    assert np.abs(dq[0]).max() <= 1e-6
+    dof = oracle.from_half_bits(bits[3], dtype)
+    # last key is seen by the last query only: dV[n-1] = P[n-1, n-1] * dO[n-1]
+    ratio = dv[-1] / dof[-1]
+    assert np.ptp(ratio) <= 2e-2 * abs(ratio.mean()) and 0 < ratio.mean() <= 1.0
+
+
+def test_backward_workspace_and_argument_errors(fa):
+    import torch
+
+    n, d = 128, 64
+    t = torch.zeros((n, d), dtype=torch.int16, device="cuda")
+    g = torch.zeros((n, d), device="cuda")
+    L = torch.zeros((n,), device="cuda")
+    with pytest.raises(fa.FlashAttnError, match="workspace"):
+        fa.flash_attention_backward(t, t, t, t, t, L, g, g, g, n, d, 0.125, n * d, n * d, False, 1, 1, fa.BF16, None, 0)
+    ws = torch.zeros(16, dtype=torch.uint8, device="cuda")
+    with pytest.raises(fa.FlashAttnError, match="workspace"):
+        fa.flash_attention_backward(t, t, t, t, t, L, g, g, g, n, d, 0.125, n * d, n * d, False, 1, 1, fa.BF16, ws, 16)
+
+
+@pytest.mark.parametrize("causal", [True])
+def test_backward_flagship_shape_sampled(fa, causal):
+    """BASELINE config 3 (bf16, H=16, N=16384, d=128): sampled rows of dQ and sampled keys of
+    dK/dV recomputed in fp64 from the same inputs."""
+    import torch
+
+    B, H, n, d = 1, 16, 16384, 128
+    scale = float(1.0 / np.sqrt(d))
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    Q, K, V, dO = (torch.rand((B, H, n, d), device="cuda", generator=gen).mul_(2).sub_(1).to(torch.bfloat16) for _ in range(4))
+    O = torch.empty_like(Q)
+    L = torch.empty((B, H, n), device="cuda")
+    fa.flash_attention_v4_half(Q, K, V, O, n, d, scale, H * n * d, n * d, L, causal, B, H, fa.BF16)
+    dQ, dK, dV = (torch.empty((B, H, n, d), device="cuda") for _ in range(3))
+    wsb = fa.workspace_bytes_backward(n, d, B, H)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    fa.flash_attention_backward(Q, K, V, O, dO, L, dQ, dK, dV, n, d, scale, H * n * d, n * d, causal, B, H, fa.BF16, ws, wsb)
+    torch.cuda.synchronize()
+    for h in (0, 9):
+        q, k, v, do = (t[0, h].double() for t in (Q, K, V, dO))
+        s = (q @ k.T) * scale
+        if causal:
+            s = s.masked_fill(torch.ones(n, n, dtype=torch.bool, device="cuda").triu(1), float("-inf"))
+        p = torch.softmax(s, dim=1)
+        dp = do @ v.T
+        ds = p * (dp - (dp * p).sum(1, keepdim=True)) * scale
+        for got, want in ((dQ[0, h], ds @ k), (dK[0, h], ds.T @ q), (dV[0, h], p.T @ do)):
+            err = (got.double() - want).abs().max().item()
+            assert err <= TOL_ABS and err <= TOL_REL[oracle.BF16] * want.abs().max().item()
+        del s, p, dp, ds
