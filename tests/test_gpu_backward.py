@@ -75,16 +75,27 @@ def test_backward_matches_oracle(fa, dtype, causal, n, d):
     check([g[0, 0] for g in got], want, dtype)
 
 
-def test_backward_reference_harness_inputs(fa, golden):
-    """The reference's own backward check (main.mm:946-967, 1087-1195): N=128, D=64, fp16,
-    Q = K = V = dO = 0.01 * initRandom.  Compared with the frozen output of the reference's CPU
-    loops (decoded correctly); the bar is relative because the signal is ~1e-7."""
+@pytest.mark.parametrize("dtype", [oracle.FP16, oracle.BF16])
+def test_backward_reference_harness_inputs(fa, golden, dtype):
+    """The reference's own backward check (main.mm:946-967, 1087-1195): N=128, D=64,
+    Q = K = V = dO = 0.01 * initRandom.  fp16 is compared with the frozen output of the
+    reference's CPU loops (decoded correctly).  The bar is relative because the signal is
+    ~1e-7 (the reference's absolute 1e-1, main.mm:1191, is vacuous).  With these inputs dS is
+    ~1e-6, i.e. *subnormal* in fp16 (spacing 6e-8), so an fp16 operand path -- the reference's
+    kernel included -- cannot do better than a few percent here; bf16 has the range and meets 1 %."""
     n, d = 128, 64
-    qb = golden["bwd128_qbits"]
-    got = run_backward(fa, (qb, qb, qb, qb), n, d, 0.125, False, oracle.FP16)
-    for g, key in zip(got, ("bwd128_dq", "bwd128_dk", "bwd128_dv")):
-        w = golden[key]
-        assert np.abs(g[0, 0] - w).max() <= 5e-3 * np.abs(w).max() + 1e-12, key
+    if dtype == oracle.FP16:
+        qb = golden["bwd128_qbits"]
+        want = [golden[k] for k in ("bwd128_dq", "bwd128_dk", "bwd128_dv")]
+        tol = 6e-2
+    else:
+        qb = oracle.to_half_bits(oracle.init_random(n * d).reshape(n, d) * np.float32(0.01), dtype)
+        qf = oracle.from_half_bits(qb, dtype)
+        want = oracle.backward(qf, qf, qf, qf, 0.125, False)
+        tol = 1e-2
+    got = run_backward(fa, (qb, qb, qb, qb), n, d, 0.125, False, dtype)
+    for g, w in zip(got, want):
+        assert np.abs(g[0, 0] - w).max() <= tol * np.abs(w).max() + 1e-12
 
 
 @pytest.mark.parametrize("causal", [False, True])
