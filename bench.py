@@ -53,84 +53,127 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML DURING the timed region (a polling
+    thread, ~2 ms period); falls back to one nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.samples, self._stop, self._thr = index, [], threading.Event(), None
+        self.nv = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml as nv
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append((time.time(), line.strip()))
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.smax = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+            return
+        self._thr = threading.Thread(target=self._poll, daemon=True)
+        self._thr.start()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            try:
+                return int(ids[self.index])
+            except (ValueError, IndexError):
+                pass
+        return self.index
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.time(), sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self, t0: float, t1: float):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [l for (t, l) in self.lines if t0 - 0.05 <= t <= t1 + 0.15] or [l for (_, l) in self.lines]
-        sm, smax, reasons, power = [], [], set(), []
-        for l in rows:
-            f = [x.strip() for x in l.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if self.nv is None:
+            return self._smi_fallback()
+        self._stop.set()
+        self._thr.join(timeout=1.0)
+        nv = self.nv
+        rows = [x for x in self.samples if t0 <= x[0] <= t1] or self.samples[-3:]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(n for n, bit in names.items() if any(r[2] & bit for r in rows))
+        sm = [r[1] for r in rows]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.smax,
+                "power_w_max": max((r[3] for r in rows), default=None), "samples": len(rows), "reasons": reasons}
+
+    def _smi_fallback(self):
+        try:
+            out = subprocess.check_output(
+                ["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                text=True).strip().split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "samples": 1, "reasons": ["nvml unavailable: single nvidia-smi sample after the run"]}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no clock source available"]}
 
 
 # ---------------------------------------------------------------------------------
 # reference arm: the reference's own CPU implementation of the path on host cores
 # ---------------------------------------------------------------------------------
-def cpu_forward_sample(n: int, heads: int, threads: int, prefer_ref: bool = True):
-    """Causal forward over `heads` independent heads of length n, d=128, on `threads` host
-    threads.  Uses oracle/_ref (the reference's loops compiled from main.mm:550-578) when
-    present, else the oracle port.  Returns (seconds, flops, kind)."""
+def cpu_step_sample(n: int, heads: int, threads: int, prefer_ref: bool = True):
+    """One CPU "step" (forward + backward) over `heads` independent heads of length n, d=128, on
+    `threads` host threads.  Returns (seconds, flops, kind, description).
+
+    kind "reference": the reference's own CPU verifier loops compiled from main.mm into
+    oracle/_ref -- causal forward (main.mm:550-578) and its backward (main.mm:1092-1179, which
+    exists only non-causal with K = V = Q); one head per host thread (the loops are serial).
+    kind "port": the oracle restatement (oracle/cpu_ref.c), causal forward and causal backward,
+    OpenMP over rows."""
     import numpy as np
 
     import oracle
 
     scale = float(D ** -0.5)
     rng = np.random.default_rng(0)
-    q, k, v = (rng.uniform(-1, 1, (heads, n, D)).astype(np.float32) for _ in range(3))
-    o = np.empty_like(q)
+    q, k, v, do = (rng.uniform(-1, 1, (heads, n, D)).astype(np.float32) for _ in range(4))
     use_ref = prefer_ref and oracle.have_ref()
     if use_ref:
         R = oracle.ref()
         from concurrent.futures import ThreadPoolExecutor
 
-        def one(hh):
-            R.ref_forward_causal(q[hh], k[hh], v[hh], o[hh], n, D, scale)  # ctypes drops the GIL
+        o = np.empty_like(q)
+        qb = oracle.to_half_bits(q, oracle.FP16)
+        dob = oracle.to_half_bits(do, oracle.FP16)
+        g = [np.empty_like(q) for _ in range(3)]
+
+        def one(hh):  # ctypes drops the GIL
+            R.ref_forward_causal(q[hh], k[hh], v[hh], o[hh], n, D, scale)
+            R.ref_backward(qb[hh].reshape(-1), dob[hh].reshape(-1), g[0][hh], g[1][hh], g[2][hh], n, D, scale)
 
         t0 = time.perf_counter()
         with ThreadPoolExecutor(max_workers=threads) as ex:
             list(ex.map(one, range(heads)))
         dt = time.perf_counter() - t0
-    else:
-        oracle.lib().oracle_set_num_threads(threads)
-        t0 = time.perf_counter()
-        for hh in range(heads):
-            oracle.forward(q[hh], k[hh], v[hh], scale, True)
-        dt = time.perf_counter() - t0
-    return dt, fwd_flops(1, heads, n, D, True), ("reference" if use_ref else "port")
+        flops = fwd_flops(1, heads, n, D, True) + 2.5 * fwd_flops(1, heads, n, D, False)
+        desc = (f"{heads} independent heads x N={n} x d={D} per step, fp32: reference CPU loops compiled from main.mm into "
+                f"oracle/_ref -- causal forward (main.mm:550-578) + its non-causal backward (main.mm:1092-1179); "
+                f"one head per host thread")
+        return dt, flops, "reference", desc
+    oracle.lib().oracle_set_num_threads(threads)
+    t0 = time.perf_counter()
+    for hh in range(heads):
+        oracle.forward(q[hh], k[hh], v[hh], scale, True)
+        oracle.backward(q[hh], k[hh], v[hh], do[hh], scale, True)
+    dt = time.perf_counter() - t0
+    desc = (f"{heads} heads x N={n} x d={D}, fp32 oracle port (oracle/cpu_ref.c): causal forward + causal backward, "
+            f"OpenMP over rows on {threads} threads")
+    return dt, 3.5 * fwd_flops(1, heads, n, D, True), "port", desc
 
 
 def run_reference(args):
@@ -138,20 +181,16 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n_s = 2048
+    n_s = 512  # the reference's backward decodes fp16 inside its inner loops: ~2 s per head at N=512
     heads = cores
-    for _ in range(args.warmup):
-        cpu_forward_sample(512, heads, cores)
-    times = []
-    kind = "port"
+    for _ in range(min(args.warmup, 2)):
+        cpu_step_sample(256, heads, cores)
+    total, flops_total, kind, sample = 0.0, 0.0, "port", ""
     for _ in range(args.steps):
-        dt, flops, kind = cpu_forward_sample(n_s, heads, cores)
-        times.append(dt)
-    total = sum(times)
-    value = flops * args.steps / total / 1e12
-    sample = (f"forward only, causal, fp32, {heads} independent heads x N={n_s} x d={D} per step "
-              f"({'reference CPU loops main.mm:550-578 compiled into oracle/_ref' if kind == 'reference' else 'oracle port'}, "
-              f"one head per host thread)")
+        dt, flops, kind, sample = cpu_step_sample(n_s, heads, cores)
+        total += dt
+        flops_total += flops
+    value = flops_total / total / 1e12
     line = {
         "impl": "reference", "metric": "attention_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -225,7 +264,6 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.25)
     # K steps; an event after each pass so forward and backward are also known separately
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     fa.reset_launch_count()
@@ -253,34 +291,48 @@ def run_ours(args):
     step_flops = fwd_flops() * (3.5 if have_bwd else 1.0)
     value = step_flops * world / (ms_per_step * 1e-3) / 1e12
 
-    # ---- e2e: host buffers in, host buffers out, through the host-buffer C-ABI call ----
+    # ---- e2e: the same step (forward + backward) with HOST buffers in and out, through the
+    #      host-buffer C-ABI call: pinned Q,K,V,dO -> device, kernels, O,L,dQ,dK,dV -> host ----
     e2e = None
     if not args.no_e2e:
-        hq, hk, hv = (torch.empty((B, H, N, D), dtype=torch.bfloat16).pin_memory() for _ in range(3))
-        for hsrc, dsrc in ((hq, Q), (hk, K), (hv, V)):
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+        hq, hk, hv, hdo = (pin((B, H, N, D), torch.bfloat16) for _ in range(4))
+        for hsrc, dsrc in ((hq, Q), (hk, K), (hv, V), (hdo, dO)):
             hsrc.copy_(dsrc)
-        ho = torch.empty((B, H, N, D), dtype=torch.bfloat16).pin_memory()
-        hl = torch.empty((B, H, N), dtype=torch.float32).pin_memory()
-        call = lambda: fa.host_attention_half(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), hl.data_ptr(),
-                                              N, D, scale, CAUSAL, B, H, fa.BF16)
+        ho = pin((B, H, N, D), torch.bfloat16)
+        hl = pin((B, H, N), torch.float32)
+        nbytes = B * H * N * D * 2
+        if have_bwd:
+            hg = [pin((B, H, N, D), torch.float32) for _ in range(3)]
+            call = lambda: fa.host_attention_fwd_bwd_half(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), hdo.data_ptr(),
+                                                          ho.data_ptr(), hl.data_ptr(), hg[0].data_ptr(), hg[1].data_ptr(),
+                                                          hg[2].data_ptr(), N, D, scale, CAUSAL, B, H, fa.BF16)
+            h2d, d2h = 4 * nbytes, nbytes + B * H * N * 4 + 3 * 2 * nbytes
+        else:
+            call = lambda: fa.host_attention_half(hq.data_ptr(), hk.data_ptr(), hv.data_ptr(), ho.data_ptr(), hl.data_ptr(),
+                                                  N, D, scale, CAUSAL, B, H, fa.BF16)
+            h2d, d2h = 3 * nbytes, nbytes + B * H * N * 4
         for _ in range(2):
             call()
         barrier()
         w0 = time.perf_counter()
         esteps = max(3, min(args.steps, 10))
         for _ in range(esteps):
-            call()  # synchronous: returns after the D2H copy of O and L
+            call()  # synchronous: returns after the last device->host copy has landed
         barrier()
         e_ms = (time.perf_counter() - w0) * 1e3 / esteps
         if world > 1:
             t = torch.tensor([e_ms], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e_ms = float(t.item())
-        nbytes = B * H * N * D * 2
-        e2e = {"value": fwd_flops() * world / (e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": 3 * nbytes, "d2h_bytes_per_step": nbytes + B * H * N * 4,
-               "what": "forward only through fa_host_attention_half (pinned host Q,K,V -> device, kernel, O and L -> host)"}
-        assert torch.equal(ho.cuda(), O), "e2e result differs from the device-resident result"
+        e2e = {"value": step_flops * world / (e_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": esteps,
+               "pcie_gbs": (h2d + d2h) / (e_ms * 1e-3) / 1e9,
+               "what": ("forward+backward" if have_bwd else "forward") + " through the host-buffer C-ABI call "
+                       "(pinned host inputs -> device, kernels, every output -> host; copies pipelined over head groups)"}
+        assert torch.equal(ho.cuda(), O), "e2e forward result differs from the device-resident result"
+        if have_bwd:
+            assert torch.equal(hg[0].cuda(), dQ), "e2e dQ differs from the device-resident result"
 
     if rank != 0:
         if world > 1:
@@ -295,6 +347,11 @@ def run_ours(args):
             "peak_source": peaks["source"] + " (cuBLAS bf16 burst)", "frac_of_nominal_2250": fwd_tf / 2250.0,
             "frac_of_sustained": fwd_tf / peaks["bf16_tflops_sustained"] if peaks["bf16_tflops_sustained"] else None,
             "traffic": None, "flops_per_launch": fwd_flops(), "launch_ms": fwd_ms}
+    if have_bwd:
+        # the backward recomputes S and dP in both of its kernels: 7 GEMM-units of work for the 5 counted
+        roof["backward"] = {"kernels": "bwd_dkdv_kernel + bwd_dq_kernel (+ bwd_delta_kernel)", "achieved": bwd_tf,
+                            "frac": bwd_tf / peaks["bf16_tflops"], "issued_mma_tflops": bwd_tf * 7.0 / 5.0,
+                            "issued_frac": bwd_tf * 7.0 / 5.0 / peaks["bf16_tflops"], "launch_ms": bwd_ms}
     prof = os.path.join(ROOT, "profiles", "fwd_traffic.json")
     if os.path.exists(prof):
         roof["traffic"] = json.load(open(prof)).get("dram_bytes_per_launch")
@@ -302,11 +359,9 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu:
         cores = os.cpu_count() or 1
-        # bounded sample: ~10-30 s of CPU work on the host cores
-        n_s = 4096
-        dt, flops, kind = cpu_forward_sample(n_s, cores, cores, prefer_ref=False)
-        cpu = {"value": flops / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": kind, "seconds": dt,
-               "sample": f"forward only, causal, fp32 oracle port (OpenMP over rows), {cores} heads x N={n_s} x d={D}"}
+        # bounded sample of the same step (forward + backward), ~10-30 s of CPU work
+        dt, flops, kind, desc = cpu_step_sample(2048, max(2, cores // 4), cores, prefer_ref=False)
+        cpu = {"value": flops / dt / 1e12, "unit": "TFLOP/s", "cores": cores, "kind": kind, "seconds": dt, "sample": desc}
 
     line = {
         "metric": "attention_tflops", "value": value, "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps,

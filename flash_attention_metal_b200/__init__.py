@@ -25,6 +25,7 @@ EXPORTS = (
     "naive_attention", "flash_attention", "flash_attention_v2", "flash_attention_v2_batched",
     "flash_attention_simd", "flash_attention_v4_half", "flash_attention_backward",
     "fa_workspace_bytes_backward", "fa_host_attention_f32", "fa_host_attention_half",
+    "fa_host_attention_fwd_bwd_half", "fa_host_release",
     "fa_last_error", "fa_version", "fa_device_count", "fa_launch_count", "fa_reset_launch_count",
 )
 
@@ -62,6 +63,8 @@ def lib() -> C.CDLL:
         L.fa_workspace_bytes_backward.restype = sz
         L.fa_host_attention_f32.argtypes = [i32, vp, vp, vp, vp, i32, i32, f32, i32]
         L.fa_host_attention_half.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, i32, i32]
+        L.fa_host_attention_fwd_bwd_half.argtypes = [vp] * 9 + [i32, i32, f32, i32, i32, i32, i32]
+        L.fa_host_release.restype = None
         L.fa_last_error.restype = C.c_char_p
         L.fa_launch_count.restype = C.c_long
         L.fa_reset_launch_count.restype = None
@@ -154,6 +157,15 @@ def host_attention_f32(variant, Q, K, V, O, N, D, scale, is_causal=False):
 def host_attention_half(Q, K, V, O, L_out, N, D, scale, is_causal, B, H, dtype):
     _check(lib().fa_host_attention_half(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(L_out), N, D, scale,
                                         int(is_causal), B, H, dtype))
+
+
+def host_attention_fwd_bwd_half(Q, K, V, dO, O, L_out, dQ, dK, dV, N, D, scale, is_causal, B, H, dtype):
+    _check(lib().fa_host_attention_fwd_bwd_half(_ptr(Q), _ptr(K), _ptr(V), _ptr(dO), _ptr(O), _ptr(L_out), _ptr(dQ),
+                                                _ptr(dK), _ptr(dV), N, D, scale, int(is_causal), B, H, dtype))
+
+
+def host_release() -> None:
+    lib().fa_host_release()
 
 
 def launch_count() -> int:

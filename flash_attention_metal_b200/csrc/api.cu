@@ -93,57 +93,4 @@ size_t fa_workspace_bytes_backward(int N, int D, int B, int H) {
   return (bytes + 255) & ~(size_t)255;
 }
 
-// ---- host-buffer entry points ------------------------------------------------
-namespace {
-struct DevBuf {
-  void *p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t n) { return cudaMalloc(&p, n); }
-};
-}  // namespace
-
-int fa_host_attention_f32(int variant, const float *Q, const float *K, const float *V, float *O,
-                          int N, int D, float scale, int is_causal) {
-  FA_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0, 1 or 2");
-  FA_REQUIRE(Q && K && V && O && N >= 1 && D >= 1, "bad arguments");
-  const size_t bytes = (size_t)N * D * sizeof(float);
-  DevBuf q, k, v, o;
-  FA_CUDA_CHECK(q.alloc(bytes));
-  FA_CUDA_CHECK(k.alloc(bytes));
-  FA_CUDA_CHECK(v.alloc(bytes));
-  FA_CUDA_CHECK(o.alloc(bytes));
-  FA_CUDA_CHECK(cudaMemcpyAsync(q.p, Q, bytes, cudaMemcpyHostToDevice, 0));
-  FA_CUDA_CHECK(cudaMemcpyAsync(k.p, K, bytes, cudaMemcpyHostToDevice, 0));
-  FA_CUDA_CHECK(cudaMemcpyAsync(v.p, V, bytes, cudaMemcpyHostToDevice, 0));
-  int rc = launch_fp32(variant, (const float *)q.p, (const float *)k.p, (const float *)v.p,
-                       (float *)o.p, N, D, scale, 0, 0, is_causal, 1, 1, 0);
-  if (rc != FA_OK) return rc;
-  FA_CUDA_CHECK(cudaMemcpyAsync(O, o.p, bytes, cudaMemcpyDeviceToHost, 0));
-  FA_CUDA_CHECK(cudaStreamSynchronize(0));
-  return FA_OK;
-}
-
-int fa_host_attention_half(const void *Q, const void *K, const void *V, void *O, float *L_out,
-                           int N, int D, float scale, int is_causal, int B, int H, int dtype) {
-  FA_REQUIRE(Q && K && V && O && N >= 1 && D >= 1 && B >= 1 && H >= 1, "bad arguments");
-  const size_t bytes = (size_t)B * H * N * D * 2;
-  const size_t lbytes = (size_t)B * H * N * sizeof(float);
-  DevBuf q, k, v, o, l;
-  FA_CUDA_CHECK(q.alloc(bytes));
-  FA_CUDA_CHECK(k.alloc(bytes));
-  FA_CUDA_CHECK(v.alloc(bytes));
-  FA_CUDA_CHECK(o.alloc(bytes));
-  if (L_out) FA_CUDA_CHECK(l.alloc(lbytes));
-  FA_CUDA_CHECK(cudaMemcpyAsync(q.p, Q, bytes, cudaMemcpyHostToDevice, 0));
-  FA_CUDA_CHECK(cudaMemcpyAsync(k.p, K, bytes, cudaMemcpyHostToDevice, 0));
-  FA_CUDA_CHECK(cudaMemcpyAsync(v.p, V, bytes, cudaMemcpyHostToDevice, 0));
-  int rc = launch_fwd_tc(q.p, k.p, v.p, o.p, (float *)l.p, N, D, scale, (int64_t)H * N * D,
-                         (int64_t)N * D, is_causal, B, H, dtype, 0);
-  if (rc != FA_OK) return rc;
-  FA_CUDA_CHECK(cudaMemcpyAsync(O, o.p, bytes, cudaMemcpyDeviceToHost, 0));
-  if (L_out) FA_CUDA_CHECK(cudaMemcpyAsync(L_out, l.p, lbytes, cudaMemcpyDeviceToHost, 0));
-  FA_CUDA_CHECK(cudaStreamSynchronize(0));
-  return FA_OK;
-}
-
 }  // extern "C"

@@ -1,0 +1,190 @@
+// Host-buffer entry points (fa_host_*): the one-call form for a caller whose tensors live
+// in host memory, as the reference's do (MTLResourceStorageModeShared, main.mm:104-115).
+//
+// Device scratch comes from a process-wide grow-only pool (released by fa_host_release), so
+// repeated calls do not pay cudaMalloc.  The 16-bit calls are pipelined over groups of heads
+// on three streams -- host->device copies of group g+1, kernels of group g and device->host
+// copies of group g-1 overlap -- because heads are independent (kernels.metal:622).  Pass
+// pinned host memory (cudaHostAlloc / cudaHostRegister) for full PCIe speed; pageable memory
+// works but serialises the copies.
+#include <cuda_runtime.h>
+
+#include <mutex>
+
+#include "fa_internal.h"
+
+namespace fa {
+namespace {
+
+struct HostPool {
+  static constexpr int kSlots = 12;
+  void *ptr[kSlots] = {};
+  size_t cap[kSlots] = {};
+  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  static constexpr int kMaxGroups = 64;
+  cudaEvent_t in_done[kMaxGroups] = {}, run_done[kMaxGroups] = {};
+  int device = -1;
+  std::mutex mu;
+
+  int ensure_device() {
+    int dev = 0;
+    FA_CUDA_CHECK(cudaGetDevice(&dev));
+    if (device != dev) {
+      release();
+      device = dev;
+    }
+    if (!s_in) {
+      FA_CUDA_CHECK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+      FA_CUDA_CHECK(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
+      FA_CUDA_CHECK(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+      for (int i = 0; i < kMaxGroups; ++i) {
+        FA_CUDA_CHECK(cudaEventCreateWithFlags(&in_done[i], cudaEventDisableTiming));
+        FA_CUDA_CHECK(cudaEventCreateWithFlags(&run_done[i], cudaEventDisableTiming));
+      }
+    }
+    return FA_OK;
+  }
+  int get(int slot, size_t bytes, void **out) {
+    if (cap[slot] < bytes) {
+      if (ptr[slot]) cudaFree(ptr[slot]);
+      ptr[slot] = nullptr;
+      cap[slot] = 0;
+      FA_CUDA_CHECK(cudaMalloc(&ptr[slot], bytes));
+      cap[slot] = bytes;
+    }
+    *out = ptr[slot];
+    return FA_OK;
+  }
+  void release() {
+    for (int i = 0; i < kSlots; ++i) {
+      if (ptr[i]) cudaFree(ptr[i]);
+      ptr[i] = nullptr;
+      cap[i] = 0;
+    }
+    if (s_in) {
+      cudaStreamDestroy(s_in); cudaStreamDestroy(s_run); cudaStreamDestroy(s_out);
+      for (int i = 0; i < kMaxGroups; ++i) { cudaEventDestroy(in_done[i]); cudaEventDestroy(run_done[i]); }
+      s_in = s_run = s_out = nullptr;
+    }
+  }
+};
+
+HostPool g_pool;
+
+int host_half_impl(const void *Q, const void *K, const void *V, const void *dO, void *O, float *L,
+                   float *dQ, float *dK, float *dV, int N, int D, float scale, int is_causal, int B,
+                   int H, int dtype) {
+  const bool bwd = dO != nullptr;
+  FA_REQUIRE(Q && K && V && O && N >= 1 && B >= 1 && H >= 1, "bad arguments");
+  FA_REQUIRE(D == 64 || D == 128, "D must be 64 or 128 (got %d)", D);
+  FA_REQUIRE(!bwd || (dQ && dK && dV), "backward needs dQ, dK and dV");
+  std::lock_guard<std::mutex> lock(g_pool.mu);
+  int rc = g_pool.ensure_device();
+  if (rc != FA_OK) return rc;
+  const int heads = B * H;
+  const size_t head_elems = (size_t)N * D;
+  const size_t hb = head_elems * 2, hf = head_elems * 4, hl = (size_t)N * 4;
+  void *dq_, *dk_, *dv_, *do_, *dOut, *dL, *gQ = nullptr, *gK = nullptr, *gV = nullptr, *dDelta = nullptr;
+  if ((rc = g_pool.get(0, heads * hb, &dq_)) || (rc = g_pool.get(1, heads * hb, &dk_)) ||
+      (rc = g_pool.get(2, heads * hb, &dv_)) || (rc = g_pool.get(3, heads * hb, &dOut)) ||
+      (rc = g_pool.get(4, heads * hl, &dL)))
+    return rc;
+  do_ = nullptr;
+  if (bwd) {
+    if ((rc = g_pool.get(5, heads * hb, &do_)) || (rc = g_pool.get(6, heads * hf, &gQ)) ||
+        (rc = g_pool.get(7, heads * hf, &gK)) || (rc = g_pool.get(8, heads * hf, &gV)) ||
+        (rc = g_pool.get(9, fa_workspace_bytes_backward(N, D, 1, heads) + 256, &dDelta)))
+      return rc;
+  }
+  // groups of heads: enough CTAs per group to fill the GPU, enough groups to overlap copies
+  int per_group = (heads + 7) / 8;
+  const int min_heads = (int)((148 * 256 + N - 1) / N);  // ~one wave of 256-row CTAs
+  if (per_group < min_heads) per_group = min_heads;
+  if (per_group > heads) per_group = heads;
+  int groups = (heads + per_group - 1) / per_group;
+  if (groups > HostPool::kMaxGroups) { groups = HostPool::kMaxGroups; per_group = (heads + groups - 1) / groups; groups = (heads + per_group - 1) / per_group; }
+  auto at = [](const void *p, size_t off) { return (const void *)((const char *)p + off); };
+  auto atw = [](void *p, size_t off) { return (void *)((char *)p + off); };
+  for (int g = 0; g < groups; ++g) {
+    const int h0 = g * per_group, nh = (h0 + per_group <= heads ? per_group : heads - h0);
+    const size_t ob = (size_t)h0 * hb, of = (size_t)h0 * hf, ol = (size_t)h0 * hl;
+    FA_CUDA_CHECK(cudaMemcpyAsync(atw(dq_, ob), at(Q, ob), nh * hb, cudaMemcpyHostToDevice, g_pool.s_in));
+    FA_CUDA_CHECK(cudaMemcpyAsync(atw(dk_, ob), at(K, ob), nh * hb, cudaMemcpyHostToDevice, g_pool.s_in));
+    FA_CUDA_CHECK(cudaMemcpyAsync(atw(dv_, ob), at(V, ob), nh * hb, cudaMemcpyHostToDevice, g_pool.s_in));
+    if (bwd) FA_CUDA_CHECK(cudaMemcpyAsync(atw(do_, ob), at(dO, ob), nh * hb, cudaMemcpyHostToDevice, g_pool.s_in));
+    FA_CUDA_CHECK(cudaEventRecord(g_pool.in_done[g], g_pool.s_in));
+    FA_CUDA_CHECK(cudaStreamWaitEvent(g_pool.s_run, g_pool.in_done[g], 0));
+    rc = launch_fwd_tc(atw(dq_, ob), atw(dk_, ob), atw(dv_, ob), atw(dOut, ob), (float *)atw(dL, ol), N, D, scale,
+                       (int64_t)nh * head_elems, (int64_t)head_elems, is_causal, 1, nh, dtype, g_pool.s_run);
+    if (rc != FA_OK) return rc;
+    if (bwd) {
+      rc = launch_bwd_tc(atw(dq_, ob), atw(dk_, ob), atw(dv_, ob), atw(dOut, ob), atw(do_, ob), (float *)atw(dL, ol),
+                         (float *)atw(gQ, of), (float *)atw(gK, of), (float *)atw(gV, of), N, D, scale,
+                         (int64_t)nh * head_elems, (int64_t)head_elems, is_causal, 1, nh, dtype, atw(dDelta, ol),
+                         fa_workspace_bytes_backward(N, D, 1, nh), g_pool.s_run);
+      if (rc != FA_OK) return rc;
+    }
+    FA_CUDA_CHECK(cudaEventRecord(g_pool.run_done[g], g_pool.s_run));
+    FA_CUDA_CHECK(cudaStreamWaitEvent(g_pool.s_out, g_pool.run_done[g], 0));
+    FA_CUDA_CHECK(cudaMemcpyAsync(atw(O, ob), at(dOut, ob), nh * hb, cudaMemcpyDeviceToHost, g_pool.s_out));
+    if (L) FA_CUDA_CHECK(cudaMemcpyAsync(atw(L, ol), at(dL, ol), nh * hl, cudaMemcpyDeviceToHost, g_pool.s_out));
+    if (bwd) {
+      FA_CUDA_CHECK(cudaMemcpyAsync(atw(dQ, of), at(gQ, of), nh * hf, cudaMemcpyDeviceToHost, g_pool.s_out));
+      FA_CUDA_CHECK(cudaMemcpyAsync(atw(dK, of), at(gK, of), nh * hf, cudaMemcpyDeviceToHost, g_pool.s_out));
+      FA_CUDA_CHECK(cudaMemcpyAsync(atw(dV, of), at(gV, of), nh * hf, cudaMemcpyDeviceToHost, g_pool.s_out));
+    }
+  }
+  FA_CUDA_CHECK(cudaStreamSynchronize(g_pool.s_out));
+  FA_CUDA_CHECK(cudaStreamSynchronize(g_pool.s_run));
+  return FA_OK;
+}
+
+}  // namespace
+}  // namespace fa
+
+using namespace fa;
+
+extern "C" {
+
+int fa_host_attention_f32(int variant, const float *Q, const float *K, const float *V, float *O,
+                          int N, int D, float scale, int is_causal) {
+  FA_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0, 1 or 2");
+  FA_REQUIRE(Q && K && V && O && N >= 1 && D >= 1, "bad arguments");
+  std::lock_guard<std::mutex> lock(g_pool.mu);
+  int rc = g_pool.ensure_device();
+  if (rc != FA_OK) return rc;
+  const size_t bytes = (size_t)N * D * sizeof(float);
+  void *q, *k, *v, *o;
+  if ((rc = g_pool.get(0, bytes, &q)) || (rc = g_pool.get(1, bytes, &k)) || (rc = g_pool.get(2, bytes, &v)) ||
+      (rc = g_pool.get(3, bytes, &o)))
+    return rc;
+  cudaStream_t st = g_pool.s_run;
+  FA_CUDA_CHECK(cudaMemcpyAsync(q, Q, bytes, cudaMemcpyHostToDevice, st));
+  FA_CUDA_CHECK(cudaMemcpyAsync(k, K, bytes, cudaMemcpyHostToDevice, st));
+  FA_CUDA_CHECK(cudaMemcpyAsync(v, V, bytes, cudaMemcpyHostToDevice, st));
+  rc = launch_fp32(variant, (const float *)q, (const float *)k, (const float *)v, (float *)o, N, D, scale, 0, 0,
+                   is_causal, 1, 1, st);
+  if (rc != FA_OK) return rc;
+  FA_CUDA_CHECK(cudaMemcpyAsync(O, o, bytes, cudaMemcpyDeviceToHost, st));
+  FA_CUDA_CHECK(cudaStreamSynchronize(st));
+  return FA_OK;
+}
+
+int fa_host_attention_half(const void *Q, const void *K, const void *V, void *O, float *L_out,
+                           int N, int D, float scale, int is_causal, int B, int H, int dtype) {
+  return host_half_impl(Q, K, V, nullptr, O, L_out, nullptr, nullptr, nullptr, N, D, scale, is_causal, B, H, dtype);
+}
+
+int fa_host_attention_fwd_bwd_half(const void *Q, const void *K, const void *V, const void *dO, void *O,
+                                   float *L_out, float *dQ, float *dK, float *dV, int N, int D, float scale,
+                                   int is_causal, int B, int H, int dtype) {
+  FA_REQUIRE(dO != nullptr, "dO is null");
+  return host_half_impl(Q, K, V, dO, O, L_out, dQ, dK, dV, N, D, scale, is_causal, B, H, dtype);
+}
+
+void fa_host_release(void) {
+  std::lock_guard<std::mutex> lock(g_pool.mu);
+  g_pool.release();
+}
+
+}  // extern "C"

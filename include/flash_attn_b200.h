@@ -115,12 +115,19 @@ size_t fa_workspace_bytes_backward(int N, int D, int B, int H);
  * The reference's buffers are MTLResourceStorageModeShared (main.mm:104-115):
  * the host writes inputs and reads outputs in place.  These calls give a
  * caller with HOST tensors the same one-call behaviour: copy in, run, copy out,
- * synchronise.  Contiguous [B, H, N, D].  They allocate device memory
- * internally per call and are meant for the harness and for end-to-end timing. */
+ * synchronise.  Contiguous [B, H, N, D].  Device scratch comes from a grow-only
+ * pool inside the library (fa_host_release frees it); the 16-bit calls pipeline
+ * copies and kernels over groups of heads.  Pinned host memory gives full PCIe
+ * speed.  These are what the harness-style caller and bench.py's end-to-end leg use. */
 int fa_host_attention_f32(int variant /*0 naive, 1 v1, 2 v2*/, const float *Q, const float *K,
                           const float *V, float *O, int N, int D, float scale, int is_causal);
 int fa_host_attention_half(const void *Q, const void *K, const void *V, void *O, float *L_out,
                            int N, int D, float scale, int is_causal, int B, int H, int dtype);
+/* forward (O, L_out) followed by backward (dQ, dK, dV in fp32) in one call */
+int fa_host_attention_fwd_bwd_half(const void *Q, const void *K, const void *V, const void *dO,
+                                   void *O, float *L_out, float *dQ, float *dK, float *dV, int N,
+                                   int D, float scale, int is_causal, int B, int H, int dtype);
+void fa_host_release(void);
 
 /* ---- support ----------------------------------------------------------------*/
 const char *fa_last_error(void);

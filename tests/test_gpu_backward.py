@@ -177,3 +177,24 @@ def test_backward_flagship_shape_sampled(fa, causal):
             err = (got.double() - want).abs().max().item()
             assert err <= TOL_ABS and err <= TOL_REL[oracle.BF16] * want.abs().max().item()
         del s, p, dp, ds
+
+
+def test_host_buffer_fwd_bwd_entry_point(fa):
+    """fa_host_attention_fwd_bwd_half: host tensors in, host tensors out, pipelined over head groups;
+    must equal the device-pointer path bit for bit."""
+    import torch
+
+    B, H, n, d, dtype = 2, 5, 512, 64, oracle.BF16
+    bits = make_bits(n, d, dtype, heads=(B, H), seeds=(11, 12, 13, 14))
+    want = run_backward(fa, bits, n, d, 0.125, True, dtype, B, H)
+    o = np.empty((B, H, n, d), np.uint16)
+    l = np.empty((B, H, n), np.float32)
+    grads = [np.empty((B, H, n, d), np.float32) for _ in range(3)]
+    fa.host_attention_fwd_bwd_half(bits[0], bits[1], bits[2], bits[3], o, l, *grads, n, d, 0.125, True, B, H, dtype)
+    for g, w in zip(grads, want):
+        assert np.array_equal(g, w)
+    f = [oracle.from_half_bits(t, dtype) for t in bits]
+    ow, lw = oracle.forward_batched(f[0], f[1], f[2], 0.125, True)
+    assert np.abs(oracle.from_half_bits(o, dtype) - ow).max() <= 2e-2
+    assert np.abs(l - lw).max() <= 5e-3
+    fa.host_release()
