@@ -1,0 +1,64 @@
+"""The harness's benchmark_results.csv must stay consumable by the reference's plot_results.py
+(SURVEY.md section 8 row f1).  tests/golden/harness_benchmark_results.csv is a real output of
+harness/flash_attn on a B200.  The parser rules are restated from plot_results.py:16-39; when the
+reference is mounted, its unmodified script is run on the file as well."""
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSV = os.path.join(ROOT, "tests", "golden", "harness_benchmark_results.csv")
+HEADER10 = "N,Naive(ms),Flash(ms),FlashV2(ms),FlashV3(ms),FlashV4(ms),SpeedupV1,SpeedupV2,SpeedupV3,SpeedupV4"
+
+
+def parse_like_plot_results(path):
+    rows, started = [], False
+    for line in open(path):
+        line = line.strip()
+        if "N,Naive(ms)" in line:          # plot_results.py:16-18
+            started = True
+            continue
+        if not started or not line:
+            continue
+        f = line.split(",")
+        if len(f) < 8:                      # plot_results.py:22
+            continue
+        n = int(f[0])
+        naive, v1, v2, v3, v4 = (float(x) for x in f[1:6])   # plot_results.py:25-32
+        if naive <= 0:                      # plot_results.py:34
+            continue
+        rows.append((n, naive / v1, naive / v2, naive / v3, naive / v4))
+    return rows
+
+
+def test_csv_header_keeps_the_reference_columns_first():
+    first = open(CSV).readline().strip()
+    assert first.startswith(HEADER10)          # main.mm:598-606
+    src = open(os.path.join(ROOT, "harness", "main.cpp")).read()
+    assert HEADER10 in src.replace('"\n      "', "")
+
+
+def test_csv_rows_parse_with_the_reference_rules():
+    rows = parse_like_plot_results(CSV)
+    assert len(rows) >= 2                      # plot_results.py divides by zero on fewer
+    assert [r[0] for r in rows] == sorted(r[0] for r in rows)
+    assert max(max(r[1:]) for r in rows) > 0
+    # on B200 every optimised variant beats the naive kernel from N=256 up
+    for n, s1, s2, s3, s4 in rows:
+        if n >= 256:
+            assert min(s1, s2, s3, s4) > 1.0
+
+
+def test_unmodified_reference_plot_script_accepts_the_csv(tmp_path):
+    script = "/root/reference/plot_results.py"
+    if not os.path.exists(script):
+        import pytest
+
+        pytest.skip("reference not mounted")
+    shutil.copy(CSV, tmp_path / "benchmark_results.csv")
+    subprocess.check_call([sys.executable, script], cwd=tmp_path, stdout=subprocess.DEVNULL)
+    svg = (tmp_path / "speedup_plot.svg").read_text()
+    assert svg.lstrip().startswith("<svg") or "<svg" in svg
+    assert len(re.findall(r"<(polyline|path|line|circle)", svg)) > 4
