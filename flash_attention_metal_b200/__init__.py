@@ -26,6 +26,8 @@ EXPORTS = (
     "flash_attention_simd", "flash_attention_v4_half", "flash_attention_backward",
     "fa_workspace_bytes_backward", "fa_host_attention_f32", "fa_host_attention_half",
     "fa_host_attention_fwd_bwd_half", "fa_host_release",
+    "flash_attention_v4_half_rect", "fa_ring_unique_id_bytes", "fa_ring_get_unique_id", "fa_ring_create",
+    "fa_ring_destroy", "fa_ring_workspace_bytes", "fa_ring_attention_forward", "fa_ring_plan", "fa_ring_local_rows",
     "fa_last_error", "fa_version", "fa_device_count", "fa_launch_count", "fa_reset_launch_count",
 )
 
@@ -68,14 +70,16 @@ def lib() -> C.CDLL:
         L.fa_last_error.restype = C.c_char_p
         L.fa_launch_count.restype = C.c_long
         L.fa_reset_launch_count.restype = None
-        if hasattr(L, "fa_ring_create"):
-            L.fa_ring_unique_id_bytes.restype = i32
-            L.fa_ring_get_unique_id.argtypes = [vp, i32]
-            L.fa_ring_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32]
-            L.fa_ring_destroy.argtypes = [vp]
-            L.fa_ring_workspace_bytes.argtypes = [i32, i32, i32, i32]
-            L.fa_ring_workspace_bytes.restype = sz
-            L.fa_ring_attention_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, i32, vp, sz, vp]
+        L.flash_attention_v4_half_rect.argtypes = [vp, vp, vp, vp, i32, i32, i32, f32, i64, i64, i64, i64, vp, i32, i32, i32, vp]
+        L.fa_ring_get_unique_id.argtypes = [vp, i32]
+        L.fa_ring_create.argtypes = [C.POINTER(vp), vp, i32, i32, i32]
+        L.fa_ring_destroy.argtypes = [vp]
+        L.fa_ring_workspace_bytes.argtypes = [i32, i32, i32, i32]
+        L.fa_ring_workspace_bytes.restype = sz
+        L.fa_ring_attention_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, i32, vp, sz, vp]
+        ip = C.POINTER(i32)
+        L.fa_ring_plan.argtypes = [i32, i32, i32, i32, i32, ip, ip, ip, ip, ip, ip]
+        L.fa_ring_local_rows.argtypes = [i32, i32, i32, i32, C.POINTER(i64), ip]
         _lib = L
     return _lib
 
@@ -135,6 +139,59 @@ def flash_attention_v4_half(Q, K, V, O, N, D, scale, batch_stride, head_stride, 
     """V4, kernels.metal:600-883 / main.mm:414-440 (buffer indices 0..10, then B, H, dtype)."""
     _check(lib().flash_attention_v4_half(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), N, D, scale, batch_stride, head_stride,
                                          _ptr(L_out), int(is_causal), B, H, dtype, _stream(stream)))
+
+
+def flash_attention_v4_half_rect(Q, K, V, O, Nq, Nk, D, scale, q_batch_stride, q_head_stride, kv_batch_stride,
+                                 kv_head_stride, L_out, B=1, H=1, dtype=FP16, stream=None):
+    """Cross-attention form (Nq != Nk, non-causal); the reference has only Nq == Nk."""
+    _check(lib().flash_attention_v4_half_rect(_ptr(Q), _ptr(K), _ptr(V), _ptr(O), Nq, Nk, D, scale, q_batch_stride,
+                                              q_head_stride, kv_batch_stride, kv_head_stride, _ptr(L_out), B, H, dtype,
+                                              _stream(stream)))
+
+
+# -- ring / context-parallel attention (one process per GPU) -----------------------
+def ring_unique_id() -> bytes:
+    n = lib().fa_ring_unique_id_bytes()
+    buf = C.create_string_buffer(n)
+    _check(lib().fa_ring_get_unique_id(buf, n))
+    return buf.raw
+
+
+class Ring:
+    """fa_ring_t wrapper.  `unique_id` comes from ring_unique_id() on rank 0 and must reach every rank."""
+
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int):
+        self.handle = C.c_void_p()
+        self.rank, self.world = rank, world
+        _check(lib().fa_ring_create(C.byref(self.handle), unique_id, rank, world, device))
+
+    def workspace_bytes(self, n_local, D, H, dtype) -> int:
+        return int(lib().fa_ring_workspace_bytes(n_local, D, H, dtype))
+
+    def forward(self, Q, K, V, O, L_out, n_local, D, H, scale, is_causal, dtype, workspace, workspace_bytes, stream=None):
+        _check(lib().fa_ring_attention_forward(self.handle, _ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(L_out), n_local, D,
+                                               H, scale, int(is_causal), dtype, _ptr(workspace), workspace_bytes,
+                                               _stream(stream)))
+
+    def close(self):
+        if self.handle:
+            lib().fa_ring_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
+def ring_plan(rank, world, step, n_local, is_causal):
+    """(src_rank, q_off, q_rows, k_off, k_rows, block_causal) of the block `rank` computes at `step`."""
+    out = [C.c_int() for _ in range(6)]
+    _check(lib().fa_ring_plan(rank, world, step, n_local, int(is_causal), *[C.byref(o) for o in out]))
+    return tuple(o.value for o in out)
+
+
+def ring_local_rows(rank, world, n_local, is_causal):
+    """[(first_global_row, rows), ...] of the chunk(s) a rank holds, in local order."""
+    first = (C.c_int64 * 2)()
+    rows = (C.c_int * 2)()
+    _check(lib().fa_ring_local_rows(rank, world, n_local, int(is_causal), first, rows))
+    return [(int(first[i]), int(rows[i])) for i in range(2) if rows[i] > 0]
 
 
 def workspace_bytes_backward(N, D, B, H) -> int:

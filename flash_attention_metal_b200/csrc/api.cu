@@ -76,6 +76,14 @@ int flash_attention_v4_half(const void *Q, const void *K, const void *V, void *O
                        dtype, (cudaStream_t)stream);
 }
 
+int flash_attention_v4_half_rect(const void *Q, const void *K, const void *V, void *O, int Nq, int Nk,
+                                 int D, float scale, int64_t q_batch_stride, int64_t q_head_stride,
+                                 int64_t kv_batch_stride, int64_t kv_head_stride, float *L_out, int B,
+                                 int H, int dtype, fa_stream_t stream) {
+  return launch_fwd_tc_rect(Q, K, V, O, L_out, Nq, Nk, D, scale, q_batch_stride, q_head_stride, kv_batch_stride,
+                            kv_head_stride, 0, B, H, dtype, (cudaStream_t)stream);
+}
+
 int flash_attention_backward(const void *Q, const void *K, const void *V, const void *O,
                              const void *dO, const float *L, float *dQ, float *dK, float *dV,
                              int N, int D, float scale, int64_t batch_stride,

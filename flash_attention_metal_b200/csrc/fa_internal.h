@@ -36,6 +36,12 @@ int launch_fwd_tc(const void *Q, const void *K, const void *V, void *O, float *L
                   float scale, int64_t batch_stride, int64_t head_stride, int is_causal, int B, int H,
                   int dtype, cudaStream_t stream);
 
+// rectangular (Nq x Nk, separate Q/O and K/V strides) form used by ring attention
+int launch_fwd_tc_rect(const void *Q, const void *K, const void *V, void *O, float *L, int Nq, int Nk,
+                       int D, float scale, int64_t q_batch_stride, int64_t q_head_stride,
+                       int64_t kv_batch_stride, int64_t kv_head_stride, int is_causal, int B, int H,
+                       int dtype, cudaStream_t stream);
+
 // backward (bwd_tc.cu)
 int launch_bwd_tc(const void *Q, const void *K, const void *V, const void *O, const void *dO,
                   const float *L, float *dQ, float *dK, float *dV, int N, int D, float scale,

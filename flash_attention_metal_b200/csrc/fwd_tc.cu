@@ -59,12 +59,13 @@ struct FwdCfg {
 struct FwdParams {
   void *O;
   float *L;
-  int N;
+  int Nq;             // query rows (= rows of O and L)
+  int Nk;             // keys (== Nq unless called for a rectangular ring-attention block)
   int H;
   float scale;        // multiplies the dot product
   float scale_log2;   // scale * log2(e)
-  int64_t batch_stride, head_stride;  // elements
-  int causal;
+  int64_t batch_stride, head_stride;  // elements, of Q / O
+  int causal;         // requires Nq == Nk
 };
 
 template <int D, int IS_BF16>
@@ -93,13 +94,13 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   // causal: the last row blocks have the most keys -> schedule them first
   const int qb = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
   const int q_row0 = qb * 2 * kBM;
-  const int n_kv_all = (p.N + kBN - 1) / kBN;
+  const int n_kv_all = (p.Nk + kBN - 1) / kBN;
   // KV tiles each Q tile needs (0 = tile entirely past N)
   int n_t[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int r0 = q_row0 + t * kBM;
-    n_t[t] = r0 >= p.N ? 0 : (p.causal ? min(n_kv_all, r0 / kBN + 1) : n_kv_all);
+    n_t[t] = r0 >= p.Nq ? 0 : (p.causal ? min(n_kv_all, r0 / kBN + 1) : n_kv_all);
   }
   const int nmax = max(n_t[0], n_t[1]);
 
@@ -148,9 +149,9 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
       // ---- masks: causal diagonal tile (always the last one) / keys past N ----
       const bool diag = p.causal && (j == nt - 1);
-      const bool tail = (j + 1) * kBN > p.N;
+      const bool tail = (j + 1) * kBN > p.Nk;
       if (diag || tail) {
-        int limit = p.N - 1 - j * kBN;                 // last valid key column in this tile
+        int limit = p.Nk - 1 - j * kBN;                 // last valid key column in this tile
         if (diag) limit = min(limit, grow - j * kBN);  // key <= query row
 #pragma unroll
         for (int c = 0; c < 4; ++c)
@@ -227,13 +228,13 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < 16; ++i)
           w[i] = pack2<IS_BF16>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
-        if (grow < p.N) {
+        if (grow < p.Nq) {
           uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
 #pragma unroll
           for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
         }
       }
-      if (p.L != nullptr && grow < p.N)
+      if (p.L != nullptr && grow < p.Nq)
         p.L[head_off / D + grow] = m_run * p.scale + lg2(l_run) * kLn2;
     }
   } else {
@@ -351,7 +352,7 @@ int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUt
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  dim3 grid((p.N + 2 * kBM - 1) / (2 * kBM), p.H, B);
+  dim3 grid((p.Nq + 2 * kBM - 1) / (2 * kBM), p.H, B);
   fwd_tc_kernel<D, IS_BF16><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
   FA_CUDA_CHECK(cudaGetLastError());
   count_launch();
@@ -360,41 +361,53 @@ int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUt
 
 }  // namespace
 
-int launch_fwd_tc(const void *Q, const void *K, const void *V, void *O, float *L, int N, int D,
-                  float scale, int64_t batch_stride, int64_t head_stride, int is_causal, int B, int H,
-                  int dtype, cudaStream_t stream) {
+int launch_fwd_tc_rect(const void *Q, const void *K, const void *V, void *O, float *L, int Nq, int Nk,
+                       int D, float scale, int64_t q_batch_stride, int64_t q_head_stride,
+                       int64_t kv_batch_stride, int64_t kv_head_stride, int is_causal, int B, int H,
+                       int dtype, cudaStream_t stream) {
   FA_REQUIRE(Q && K && V && O, "null tensor pointer");
-  FA_REQUIRE(N >= 1, "N must be >= 1 (got %d)", N);
+  FA_REQUIRE(Nq >= 1 && Nk >= 1, "N must be >= 1 (got %d x %d)", Nq, Nk);
+  FA_REQUIRE(!is_causal || Nq == Nk, "causal attention needs Nq == Nk");
   FA_REQUIRE(D == 64 || D == 128, "D must be 64 or 128 (got %d)", D);
   FA_REQUIRE(B >= 1 && H >= 1 && H <= 65535 && B <= 65535, "bad B/H (%d, %d)", B, H);
   FA_REQUIRE(dtype == FA_DTYPE_FP16 || dtype == FA_DTYPE_BF16, "dtype must be FA_DTYPE_FP16 or FA_DTYPE_BF16");
   FA_REQUIRE(scale > 0.f, "scale must be positive");
   FA_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O), "Q/K/V/O must be 16-byte aligned");
-  FA_REQUIRE(batch_stride % 8 == 0 && head_stride % 8 == 0, "strides must be multiples of 8 elements");
-  FA_REQUIRE((H == 1 || head_stride >= (int64_t)N * D) && (B == 1 || batch_stride >= (int64_t)N * D),
+  FA_REQUIRE(q_batch_stride % 8 == 0 && q_head_stride % 8 == 0 && kv_batch_stride % 8 == 0 && kv_head_stride % 8 == 0,
+             "strides must be multiples of 8 elements");
+  FA_REQUIRE((H == 1 || (q_head_stride >= (int64_t)Nq * D && kv_head_stride >= (int64_t)Nk * D)) &&
+                 (B == 1 || (q_batch_stride >= (int64_t)Nq * D && kv_batch_stride >= (int64_t)Nk * D)),
              "heads overlap: stride smaller than N*D");
-  FA_REQUIRE(L == nullptr || (head_stride % D == 0 && batch_stride % D == 0),
+  FA_REQUIRE(L == nullptr || (q_head_stride % D == 0 && q_batch_stride % D == 0),
              "L_out needs strides that are multiples of D (L index = offset / D, kernels.metal:623)");
   CUtensorMap tmQ, tmK, tmV;
   int rc;
-  if ((rc = make_tensor_map_bhnd(&tmQ, Q, dtype, N, D, H, B, head_stride, batch_stride, kBM)) != FA_OK) return rc;
-  if ((rc = make_tensor_map_bhnd(&tmK, K, dtype, N, D, H, B, head_stride, batch_stride, kBN)) != FA_OK) return rc;
-  if ((rc = make_tensor_map_bhnd(&tmV, V, dtype, N, D, H, B, head_stride, batch_stride, kBN)) != FA_OK) return rc;
+  if ((rc = make_tensor_map_bhnd(&tmQ, Q, dtype, Nq, D, H, B, q_head_stride, q_batch_stride, kBM)) != FA_OK) return rc;
+  if ((rc = make_tensor_map_bhnd(&tmK, K, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, kBN)) != FA_OK) return rc;
+  if ((rc = make_tensor_map_bhnd(&tmV, V, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, kBN)) != FA_OK) return rc;
   FwdParams p;
   p.O = O;
   p.L = L;
-  p.N = N;
+  p.Nq = Nq;
+  p.Nk = Nk;
   p.H = H;
   p.scale = scale;
   p.scale_log2 = scale * kLog2e;
-  p.batch_stride = batch_stride;
-  p.head_stride = head_stride;
+  p.batch_stride = q_batch_stride;
+  p.head_stride = q_head_stride;
   p.causal = is_causal ? 1 : 0;
   if (D == 64)
     return dtype == FA_DTYPE_BF16 ? launch_fwd_tc_impl<64, 1>(tmQ, tmK, tmV, p, B, stream)
                                   : launch_fwd_tc_impl<64, 0>(tmQ, tmK, tmV, p, B, stream);
   return dtype == FA_DTYPE_BF16 ? launch_fwd_tc_impl<128, 1>(tmQ, tmK, tmV, p, B, stream)
                                 : launch_fwd_tc_impl<128, 0>(tmQ, tmK, tmV, p, B, stream);
+}
+
+int launch_fwd_tc(const void *Q, const void *K, const void *V, void *O, float *L, int N, int D,
+                  float scale, int64_t batch_stride, int64_t head_stride, int is_causal, int B, int H,
+                  int dtype, cudaStream_t stream) {
+  return launch_fwd_tc_rect(Q, K, V, O, L, N, N, D, scale, batch_stride, head_stride, batch_stride, head_stride,
+                            is_causal, B, H, dtype, stream);
 }
 
 }  // namespace fa

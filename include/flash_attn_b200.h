@@ -111,6 +111,36 @@ int flash_attention_backward(const void *Q, const void *K, const void *V, const 
 
 size_t fa_workspace_bytes_backward(int N, int D, int B, int H);
 
+/* Rectangular (cross-attention) form of flash_attention_v4_half: Nq query rows against Nk
+ * keys/values, non-causal, separate strides for Q/O and K/V (the
+ * reference only has Nq == Nk).  Ring attention is built on it. */
+int flash_attention_v4_half_rect(const void *Q, const void *K, const void *V, void *O, int Nq, int Nk,
+                                 int D, float scale, int64_t q_batch_stride, int64_t q_head_stride,
+                                 int64_t kv_batch_stride, int64_t kv_head_stride, float *L_out, int B,
+                                 int H, int dtype, fa_stream_t stream);
+
+/* ---- ring / context-parallel attention across the GPUs of one box (new; not in the
+ * reference, BASELINE.json config 5).  One process per GPU.  Each rank holds n_local rows of
+ * Q, K, V per head, contiguous [H, n_local, D].  Non-causal: rank r holds global rows
+ * [r*n_local, (r+1)*n_local).  Causal: zig-zag -- with c = n_local/2, local rows [0,c) are
+ * global chunk r and local rows [c,2c) are global chunk 2*world-1-r (fa_ring_local_rows), so
+ * every rank does the same amount of unmasked work at every step.  K/V chunks rotate with
+ * NCCL send/recv over NVLink on a side stream, overlapped with the local tile loop. */
+typedef void *fa_ring_t;
+int fa_ring_unique_id_bytes(void);
+int fa_ring_get_unique_id(void *out, int bytes);            /* rank 0; ship the bytes to the others */
+int fa_ring_create(fa_ring_t *ring, const void *unique_id, int rank, int world, int device);
+int fa_ring_destroy(fa_ring_t ring);
+size_t fa_ring_workspace_bytes(int n_local, int D, int H, int dtype);
+int fa_ring_attention_forward(fa_ring_t ring, const void *Q, const void *K, const void *V, void *O,
+                              float *L_out, int n_local, int D, int H, float scale, int is_causal,
+                              int dtype, void *workspace, size_t workspace_bytes, fa_stream_t stream);
+/* host-only helpers (no GPU needed): the block a rank computes at a ring step, in local row
+ * coordinates, and the global rows a rank owns */
+int fa_ring_plan(int rank, int world, int step, int n_local, int is_causal, int *src_rank, int *q_off,
+                 int *q_rows, int *k_off, int *k_rows, int *block_causal);
+int fa_ring_local_rows(int rank, int world, int n_local, int is_causal, int64_t first_row[2], int rows[2]);
+
 /* ---- host-buffer entry points ----------------------------------------------
  * The reference's buffers are MTLResourceStorageModeShared (main.mm:104-115):
  * the host writes inputs and reads outputs in place.  These calls give a
