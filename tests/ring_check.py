@@ -1,6 +1,6 @@
 """Multi-GPU check + timing of ring attention (not a pytest file; run under torchrun):
   python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 --master-port 29511 \
-      tests/ring_check.py [--n-total N] [--heads H] [--d D] [--causal 0|1] [--check 0|1] [--reps R]
+      tests/ring_check.py [--n-total N] [--heads H] [--hdim D] [--causal 0|1] [--check 0|1] [--reps R]
 Every rank builds the same full Q/K/V (same seed), runs the single-GPU kernel on the full problem
 (when --check 1) and compares its ring output rows with it; then times the ring forward with CUDA
 events (max over ranks) and rank 0 prints one JSON line."""
@@ -13,7 +13,7 @@ import flash_attention_metal_b200 as fa
 ap = argparse.ArgumentParser()
 ap.add_argument("--n-total", type=int, default=16384)
 ap.add_argument("--heads", type=int, default=4)
-ap.add_argument("--d", type=int, default=128)
+ap.add_argument("--hdim", type=int, default=128)
 ap.add_argument("--causal", type=int, default=1)
 ap.add_argument("--check", type=int, default=1)
 ap.add_argument("--reps", type=int, default=5)
@@ -21,7 +21,7 @@ a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-H, D, N = a.heads, a.d, a.n_total
+H, D, N = a.heads, a.hdim, a.n_total
 n_local = N // world
 scale = D ** -0.5
 uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
