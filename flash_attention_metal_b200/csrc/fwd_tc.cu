@@ -193,18 +193,21 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
       // ---- P = exp2(s * scale_log2 - m * scale_log2), row sum, pack ---------------
       const float neg_m = -m_run * p.scale_log2;
-      float sum[4] = {0.f, 0.f, 0.f, 0.f};
+      // packed fp32x2 FMA / ADD: one issue slot per two elements (FFMA2 / FADD2)
+      const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2), negm2 = pack_f32x2(neg_m, neg_m);
+      uint64_t sum2[2] = {0ull, 0ull};
       uint32_t pk[2][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float p0 = ex2(fmaf(__uint_as_float(s[c][i]), p.scale_log2, neg_m));
-          const float p1 = ex2(fmaf(__uint_as_float(s[c][i + 1]), p.scale_log2, neg_m));
-          sum[(i >> 1) & 3] += p0 + p1;
+          const uint64_t x2 = fma_f32x2(pack_u32x2(s[c][i], s[c][i + 1]), scale2, negm2);
+          const float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
+          sum2[(i >> 1) & 1] = add_f32x2(sum2[(i >> 1) & 1], pack_f32x2(p0, p1));
           pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack2<IS_BF16>(p0, p1);
         }
-      l_run = l_run * acc_scale + ((sum[0] + sum[1]) + (sum[2] + sum[3]));
+      const uint64_t st2 = add_f32x2(sum2[0], sum2[1]);
+      l_run = l_run * acc_scale + (lo_f32(st2) + hi_f32(st2));
       tmem_st32(tS, pk[0]);
       tmem_st32(tS + 32, pk[1]);
       tmem_wait_st();

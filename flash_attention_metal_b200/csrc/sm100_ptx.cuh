@@ -58,8 +58,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
+#ifdef FA_DEBUG_SYNC
       printf("fa: mbarrier timeout block(%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x,
              blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+#endif
       __trap();
     }
   }
@@ -225,6 +227,41 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
   else
     asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
+// ---- packed fp32x2 arithmetic (sm_100: one issue slot for two lanes) ----
+__device__ __forceinline__ uint64_t pack_u32x2(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};\n" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  return pack_u32x2(__float_as_uint(lo), __float_as_uint(hi));
+}
+__device__ __forceinline__ float lo_f32(uint64_t v) {
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;\n" : "=r"(lo), "=r"(hi) : "l"(v));
+  return __uint_as_float(lo);
+}
+__device__ __forceinline__ float hi_f32(uint64_t v) {
+  uint32_t lo, hi;
+  asm("mov.b64 {%0, %1}, %2;\n" : "=r"(lo), "=r"(hi) : "l"(v));
+  return __uint_as_float(hi);
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;\n" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
 
