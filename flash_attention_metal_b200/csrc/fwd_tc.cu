@@ -82,11 +82,11 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemTiles);
   uint64_t *q_full = bars;                       // [2]
   uint64_t *s_full = bars + 2;                   // [2]
-  uint64_t *p_full = bars + 4;                   // [2]
-  uint64_t *o_full = bars + 6;                   // [2]
-  uint64_t *kv_full = bars + 8;                  // [kStages]
-  uint64_t *kv_empty = bars + 8 + Cfg::kStages;  // [kStages]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8 + 2 * Cfg::kStages);
+  uint64_t *p_full = bars + 4;                   // [2 tiles][2 halves of the key columns]
+  uint64_t *o_full = bars + 8;                   // [2]
+  uint64_t *kv_full = bars + 10;                 // [kStages]
+  uint64_t *kv_empty = bars + 10 + Cfg::kStages; // [kStages]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10 + 2 * Cfg::kStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -108,7 +108,8 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], kBM);
+      mbar_init(&p_full[2 * i], kBM);
+      mbar_init(&p_full[2 * i + 1], kBM);
       mbar_init(&o_full[i], 1);
     }
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -196,23 +197,33 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       // packed fp32x2 FMA / ADD: one issue slot per two elements (FFMA2 / FADD2)
       const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2), negm2 = pack_f32x2(neg_m, neg_m);
       uint64_t sum2[2] = {0ull, 0ull};
-      uint32_t pk[2][32];
+      // P is handed to the MMA warp in two halves of 64 keys: the first four k-steps of
+      // O += P V run while the second half of the exponentials is still being computed
+      // (+3.5 % at D = 128; at D = 64 the PV MMA is too short to pay for the second hand-off,
+      // so both halves are published together there).
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+      for (int hlf = 0; hlf < 2; ++hlf) {
+        uint32_t pk[32];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const uint64_t x2 = fma_f32x2(pack_u32x2(s[c][i], s[c][i + 1]), scale2, negm2);
-          const float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
-          sum2[(i >> 1) & 1] = add_f32x2(sum2[(i >> 1) & 1], pack_f32x2(p0, p1));
-          pk[c >> 1][(c & 1) * 16 + (i >> 1)] = pack2<IS_BF16>(p0, p1);
+        for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const int c = hlf * 2 + cc;
+            const uint64_t x2 = fma_f32x2(pack_u32x2(s[c][i], s[c][i + 1]), scale2, negm2);
+            const float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
+            sum2[(i >> 1) & 1] = add_f32x2(sum2[(i >> 1) & 1], pack_f32x2(p0, p1));
+            pk[cc * 16 + (i >> 1)] = pack2<IS_BF16>(p0, p1);
+          }
+        tmem_st32(tS + hlf * 32, pk);
+        if (D == 128 || hlf == 1) {
+          tmem_wait_st();
+          tc_fence_before();
+          if (D == 128) mbar_arrive(&p_full[2 * t + hlf]);
+          else { mbar_arrive(&p_full[2 * t]); mbar_arrive(&p_full[2 * t + 1]); }
         }
+      }
       const uint64_t st2 = add_f32x2(sum2[0], sum2[1]);
       l_run = l_run * acc_scale + (lo_f32(st2) + hi_f32(st2));
-      tmem_st32(tS, pk[0]);
-      tmem_st32(tS + 32, pk[1]);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_full[t]);
     }
 
     if (nt > 0) {
@@ -293,10 +304,10 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                    make_sdesc_sw128(ka + off, 16, 1024), idesc_qk, kk > 0);
           }
         };
-        auto issue_pv = [&](int t, uint32_t vstage, bool accumulate) {
+        auto issue_pv = [&](int t, int hlf, uint32_t vstage, bool accumulate) {
           const uint32_t va = sKV_addr + vstage * Cfg::kTileBytes;
 #pragma unroll
-          for (int kk = 0; kk < kBN / 16; ++kk)
+          for (int kk = hlf * 4; kk < hlf * 4 + 4; ++kk)
             mma_ts(tmem_base + 256 + t * D, tmem_base + t * kBN + kk * 8,
                    make_sdesc_sw128(va + kk * 2048, Cfg::kChunkBytes, 1024), idesc_pv,
                    (accumulate || kk > 0) ? 1u : 0u);
@@ -319,9 +330,12 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             if (j < n_t[t]) {
-              mbar_wait(&p_full[t], j & 1);
+              mbar_wait(&p_full[2 * t], j & 1);
               tc_fence_after();
-              issue_pv(t, vs, j > 0);
+              issue_pv(t, 0, vs, j > 0);
+              mbar_wait(&p_full[2 * t + 1], j & 1);
+              tc_fence_after();
+              issue_pv(t, 1, vs, j > 0);
               if (j == n_t[t] - 1) tc_commit(&o_full[t]);
             }
             if (j + 1 < n_t[t]) {
