@@ -178,18 +178,21 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tX = tmem_base + lane_off + wg * 64;
     const uint32_t tY = tmem_base + lane_off + 128 + wg * 64;
     const int key = key0 + tid;
+    // per-column statistics (L_i * log2e for threads 0-63, D_i * scale for threads 64-127) of a half
+    // tile, fetched one iteration ahead so the global-memory latency hides behind the previous tile
+    auto fetch_stat = [&](int s) -> float {
+      const int qi = (i_start + s) * 64 + (tid & 63);
+      if (s >= n || qi >= p.N) return tid < 64 ? CUDART_INF_F : 0.f;
+      return tid < 64 ? __ldg(p.L + vec_off + qi) * kLog2e : __ldg(p.delta + vec_off + qi) * p.scale;
+    };
+    float stat_next = fetch_stat(wg);
+    const uint64_t scale_log2_2 = pack_f32x2(p.scale_log2, p.scale_log2), scale_2 = pack_f32x2(p.scale, p.scale);
     int it = 0;
     for (int s = wg; s < n; s += 2, ++it) {
       const int q0 = (i_start + s) * 64;
-      // per-column statistics of this half tile -> shared memory (double-buffered per wg)
-      float *ld = sLD + (wg * 2 + (it & 1)) * 128;
-      {
-        const int qi = q0 + (tid & 63);
-        float val;
-        if (tid < 64) val = qi < p.N ? __ldg(p.L + vec_off + qi) * kLog2e : CUDART_INF_F;
-        else val = qi < p.N ? __ldg(p.delta + vec_off + qi) : 0.f;
-        ld[tid] = val;
-      }
+      float *ld = sLD + (wg * 2 + (it & 1)) * 128;  // double-buffered per warpgroup
+      ld[tid] = stat_next;
+      stat_next = fetch_stat(s + 2);
       named_bar_sync(1 + wg, 128);
       mbar_wait(&xy_full[wg], it & 1);
       tc_fence_after();
@@ -201,20 +204,21 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_ld32(tY + c * 32, y);
         tmem_wait_ld();
         uint32_t pp[16], ds[16];
+        // packed fp32x2 math: P = exp2(x*c - L*log2e), dS = P * (y*scale - D*scale)
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          const float2 l2 = *reinterpret_cast<const float2 *>(&ld[c * 32 + i]);
-          const float2 dl = *reinterpret_cast<const float2 *>(&ld[64 + c * 32 + i]);
-          float p0 = ex2(fmaf(__uint_as_float(x[i]), p.scale_log2, -l2.x));
-          float p1 = ex2(fmaf(__uint_as_float(x[i + 1]), p.scale_log2, -l2.y));
+          const uint64_t l2 = *reinterpret_cast<const uint64_t *>(&ld[c * 32 + i]);
+          const uint64_t dl = *reinterpret_cast<const uint64_t *>(&ld[64 + c * 32 + i]);
+          const uint64_t e2 = fma_f32x2(pack_u32x2(x[i], x[i + 1]), scale_log2_2, neg_f32x2(l2));
+          float p0 = ex2(lo_f32(e2)), p1 = ex2(hi_f32(e2));
           if (diag) {
             if (key > q0 + c * 32 + i) p0 = 0.f;
             if (key > q0 + c * 32 + i + 1) p1 = 0.f;
           }
-          const float d0 = p0 * (__uint_as_float(y[i]) - dl.x) * p.scale;
-          const float d1 = p1 * (__uint_as_float(y[i + 1]) - dl.y) * p.scale;
+          const uint64_t g2 = fma_f32x2(pack_u32x2(y[i], y[i + 1]), scale_2, neg_f32x2(dl));
+          const uint64_t d2 = mul_f32x2(pack_f32x2(p0, p1), g2);
           pp[i >> 1] = pack2<IS_BF16>(p0, p1);
-          ds[i >> 1] = pack2<IS_BF16>(d0, d1);
+          ds[i >> 1] = pack2<IS_BF16>(lo_f32(d2), hi_f32(d2));
         }
         tmem_st16(tX + c * 16, pp);
         tmem_st16(tY + c * 16, ds);
@@ -392,6 +396,8 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int nt = n_t[t];
     const float l2 = row < p.N ? __ldg(p.L + vec_off + row) * kLog2e : CUDART_INF_F;
     const float dl = row < p.N ? __ldg(p.delta + vec_off + row) : 0.f;
+    const uint64_t scale_log2_2 = pack_f32x2(p.scale_log2, p.scale_log2), scale_2 = pack_f32x2(p.scale, p.scale);
+    const uint64_t neg_l2_2 = pack_f32x2(-l2, -l2), neg_dls_2 = pack_f32x2(-dl * p.scale, -dl * p.scale);
     for (int s = 0; s < nt; ++s) {
       mbar_wait(&xy_full[t], s & 1);
       tc_fence_after();
@@ -406,15 +412,15 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         uint32_t ds[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2(fmaf(__uint_as_float(x[i]), p.scale_log2, -l2));
-          float p1 = ex2(fmaf(__uint_as_float(x[i + 1]), p.scale_log2, -l2));
+          const uint64_t e2 = fma_f32x2(pack_u32x2(x[i], x[i + 1]), scale_log2_2, neg_l2_2);
+          float p0 = ex2(lo_f32(e2)), p1 = ex2(hi_f32(e2));
           if (diag) {
             if (k0 + c * 32 + i > row) p0 = 0.f;
             if (k0 + c * 32 + i + 1 > row) p1 = 0.f;
           }
-          const float d0 = p0 * (__uint_as_float(y[i]) - dl) * p.scale;
-          const float d1 = p1 * (__uint_as_float(y[i + 1]) - dl) * p.scale;
-          ds[i >> 1] = pack2<IS_BF16>(d0, d1);
+          const uint64_t g2 = fma_f32x2(pack_u32x2(y[i], y[i + 1]), scale_2, neg_dls_2);
+          const uint64_t d2 = mul_f32x2(pack_f32x2(p0, p1), g2);
+          ds[i >> 1] = pack2<IS_BF16>(lo_f32(d2), hi_f32(d2));
         }
         tmem_st16(tY + c * 16, ds);
       }

@@ -249,6 +249,8 @@ __device__ __forceinline__ float hi_f32(uint64_t v) {
   asm("mov.b64 {%0, %1}, %2;\n" : "=r"(lo), "=r"(hi) : "l"(v));
   return __uint_as_float(hi);
 }
+// flips both sign bits
+__device__ __forceinline__ uint64_t neg_f32x2(uint64_t a) { return a ^ 0x8000000080000000ull; }
 __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(d) : "l"(a), "l"(b), "l"(c));
