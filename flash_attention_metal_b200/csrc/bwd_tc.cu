@@ -10,17 +10,22 @@
 //   dQ  += dS K          dK += dS^T Q
 // split into three launches so that every gradient tile has exactly one owner CTA:
 //   1. bwd_delta_kernel : D_i into the caller's workspace (warp-shuffle row sums)
-//   2. bwd_dkdv_kernel  : one CTA per 128-key tile, streams 64-row Q/dO half tiles,
+//   2. bwd_dkdv_kernel  : one CTA per 128-key tile, streams 128-row Q/dO tiles,
 //                         S^T = K Q^T and dP^T = V dO^T land transposed in TMEM so that
 //                         P^T and dS^T are directly the TMEM A operands of
 //                         dV += P^T dO and dK += dS^T Q  (4 GEMMs per tile pair)
-//   3. bwd_dq_kernel    : one CTA per 2 x 128 query rows, streams 64-row K/V half tiles,
+//   3. bwd_dq_kernel    : one CTA per 2 x 128 query rows, streams 128-row K/V tiles,
 //                         S = Q K^T, dP = dO V^T, dQ += dS K  (3 GEMMs per tile pair)
+// Every MMA is M = 128, N = 128 (or N = D): tools/mma_rate_probe.cu shows N = 64
+// shared-memory-operand MMAs run at 67 % because the A tile is re-read per 64 columns.
+// Both kernels split the element-wise work in two phases (P from S, then dS from dP) so the
+// tensor core computes dP while the exponentials run, and dV / the next S while dS is formed.
 // S and dP are recomputed in both kernels (7 GEMMs instead of 5): that is the price of
 // an atomic-free, order-independent dQ.
 //
 // Warp roles in both kernels: warps 0-3 and 4-7 are two element-wise warpgroups (one
-// thread per TMEM lane), warp 8 issues MMAs, warp 9 drives TMA.
+// thread per TMEM lane), warp 8 issues MMAs, warp 9 drives TMA, warps 10-11 only complete the
+// warpgroup so setmaxnreg can move registers to the element-wise warps.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
@@ -35,7 +40,7 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kBwdThreads = 320;
+constexpr int kBwdThreads = 384;
 constexpr int kMmaWarp = 8;
 constexpr int kLoadWarp = 9;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -90,40 +95,48 @@ __global__ void __launch_bounds__(256) bwd_delta_kernel(const uint16_t *__restri
   if (lane == 0) delta[off / D + row] = acc;
 }
 
-// Shared-memory geometry.  Every tile is a stack of [rows][64 elements] chunks (128-byte
-// rows, 128-byte swizzle) as TMA writes them.
+// Shared-memory geometry.  Every tile is [128 rows][D] stored as D/64 chunks of
+// [128 rows][64 elements] (128-byte rows, 128-byte swizzle) exactly as TMA writes them.
 template <int D>
 struct BwdCfg {
   static constexpr int kChunks = D / 64;
-  static constexpr int kChunk128 = 128 * 128;  // bytes of a 128-row chunk
-  static constexpr int kChunk64 = 64 * 128;    // bytes of a 64-row chunk
-  static constexpr int kTile128 = kChunks * kChunk128;
-  static constexpr int kTile64 = kChunks * kChunk64;
-  static constexpr int kStageBytes = 2 * kTile64;  // a streamed pair of half tiles
+  static constexpr int kChunk = 128 * 128;           // bytes of one chunk
+  static constexpr int kTile = kChunks * kChunk;     // one 128-row tile
 };
 
 // K-major operand, k-step kk (16 elements of the head dim): chunk kk/4, 32 bytes per step
-template <int CHUNK_BYTES>
 __device__ __forceinline__ uint64_t kmajor_desc(uint32_t tile_addr, int kk) {
-  return make_sdesc_sw128(tile_addr + (kk >> 2) * CHUNK_BYTES + (kk & 3) * 32, 16, 1024);
+  return make_sdesc_sw128(tile_addr + (kk >> 2) * (128 * 128) + (kk & 3) * 32, 16, 1024);
 }
-// MN-major B operand over a [rows][D] tile: k-step kk covers rows 16kk..16kk+15
-template <int CHUNK_BYTES>
+// MN-major B operand over a [128 rows][D] tile: k-step kk covers rows 16kk..16kk+15
 __device__ __forceinline__ uint64_t mnmajor_desc(uint32_t tile_addr, int kk) {
-  return make_sdesc_sw128(tile_addr + kk * 2048, CHUNK_BYTES, 1024);
+  return make_sdesc_sw128(tile_addr + kk * 2048, 128 * 128, 1024);
+}
+
+template <int D>
+__device__ __forceinline__ void tma_load_tile(unsigned char *dst, const CUtensorMap *map, uint64_t *bar, int row, int h,
+                                              int b) {
+#pragma unroll
+  for (int c = 0; c < D / 64; ++c) tma_load_4d(dst + c * (128 * 128), map, bar, c * 64, row, h, b);
 }
 
 // ---------------------------------------------------------------------------
-// 2. dK / dV : CTA owns keys [128 j, 128 j + 128); streams Q/dO half tiles of 64 rows.
-//    TMEM: X_b = S^T  [b*64, +64)      (P^T  aliases its first 32 columns)
-//          Y_b = dP^T [128 + b*64, +64) (dS^T aliases its first 32 columns)
-//          dV [256, 256+D)   dK [256+D, 256+2D)
+// 2. dK / dV : CTA owns keys [128 j, 128 j + 128); streams 128-row Q_i / dO_i tiles.
+//    TMEM: X = S^T [0,128)   Y = dP^T [128,256)   dV [256,256+D)   dK [256+D,256+2D)
+//    Warpgroup w owns query columns [64w, 64w+64) of X and Y; its 16-bit P^T / dS^T go back
+//    over the first 32 columns of its own half, so k-steps 0-3 read columns [0,32) and k-steps
+//    4-7 read columns [64,96) of X (resp. Y).
+//    MMA order:  X(0) Y(0) | P? dV(0) X(1) | dS? dK(0) Y(1) | P? dV(1) X(2) | ...
 // ---------------------------------------------------------------------------
 template <int D>
 struct DkdvCfg : BwdCfg<D> {
-  static constexpr int kStages = 4;
-  static constexpr int kSmemTiles = 2 * BwdCfg<D>::kTile128 + kStages * BwdCfg<D>::kStageBytes;
-  static constexpr int kSmemBytes = kSmemTiles + 2 * 2 * 128 * 4 /*L,D vectors*/ + 1024 + 256;
+  static constexpr int kQSlots = D == 128 ? 3 : 4;
+  static constexpr int kDoSlots = D == 128 ? 2 : 4;
+  static constexpr int kSmemTiles = (2 + kQSlots + kDoSlots) * BwdCfg<D>::kTile;
+  static constexpr int kStatBytes = 2 * 2 * 128 * 4;  // [wg][double buffer][L*log2e 64 | D*scale 64]
+  // 224 KB of tiles at D = 128: only 512 bytes of alignment slack fit under the 227 KB limit (the
+  // dynamic shared window starts 1 KB-aligned in practice; the kernel traps if it ever does not)
+  static constexpr int kSmemBytes = kSmemTiles + kStatBytes + 512 + 256;
 };
 
 template <int D, int IS_BF16>
@@ -135,33 +148,43 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  if (smem - smem_raw > 512) __trap();
   unsigned char *sK = smem;
-  unsigned char *sV = smem + Cfg::kTile128;
-  unsigned char *sStage = smem + 2 * Cfg::kTile128;  // [stage][Q half | dO half]
-  float *sLD = reinterpret_cast<float *>(smem + Cfg::kSmemTiles);  // [wg][slot][L2e 64 | delta 64]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemTiles + 2 * 2 * 128 * 4);
-  uint64_t *res_full = bars;          // [1]
-  uint64_t *acc_full = bars + 1;      // [1]
-  uint64_t *xy_full = bars + 2;       // [2]
-  uint64_t *pds_full = bars + 4;      // [2]
-  uint64_t *st_full = bars + 6;       // [kStages]
-  uint64_t *st_empty = bars + 6 + Cfg::kStages;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 6 + 2 * Cfg::kStages);
+  unsigned char *sV = smem + Cfg::kTile;
+  unsigned char *sQ = smem + 2 * Cfg::kTile;                      // [kQSlots]
+  unsigned char *sDO = sQ + Cfg::kQSlots * Cfg::kTile;            // [kDoSlots]
+  float *sLD = reinterpret_cast<float *>(smem + Cfg::kSmemTiles);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemTiles + Cfg::kStatBytes);
+  uint64_t *res_full = bars;        // K_j, V_j landed
+  uint64_t *acc_full = bars + 1;    // dV, dK final
+  uint64_t *x_full = bars + 2;      // S^T ready
+  uint64_t *y_full = bars + 3;      // dP^T ready
+  uint64_t *p_ready = bars + 4;     // P^T stored by both warpgroups
+  uint64_t *ds_ready = bars + 5;    // dS^T stored by both warpgroups
+  uint64_t *q_full = bars + 6;                       // [kQSlots]
+  uint64_t *q_empty = q_full + Cfg::kQSlots;
+  uint64_t *do_full = q_empty + Cfg::kQSlots;        // [kDoSlots]
+  uint64_t *do_empty = do_full + Cfg::kDoSlots;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(do_empty + Cfg::kDoSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int key0 = j * 128;
-  const int n_half_all = (p.N + 63) / 64;
-  const int i_start = p.causal ? 2 * j : 0;  // first 64-row query half tile that sees these keys
-  const int n = n_half_all - i_start;        // >= 1 because key0 < N
+  const int n_tiles_all = (p.N + 127) / 128;
+  const int i_start = p.causal ? j : 0;    // first query tile that sees these keys
+  const int n = n_tiles_all - i_start;     // >= 1 because key0 < N
   const int64_t head_off = (int64_t)b * p.batch_stride + (int64_t)h * p.head_stride;
   const int64_t vec_off = head_off / D;
 
   if (threadIdx.x == 0) {
     mbar_init(res_full, 1);
     mbar_init(acc_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&xy_full[i], 1); mbar_init(&pds_full[i], 128); }
-    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
+    mbar_init(x_full, 1);
+    mbar_init(y_full, 1);
+    mbar_init(p_ready, 256);
+    mbar_init(ds_ready, 256);
+    for (int i = 0; i < Cfg::kQSlots; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+    for (int i = 0; i < Cfg::kDoSlots; ++i) { mbar_init(&do_full[i], 1); mbar_init(&do_empty[i], 1); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -172,60 +195,81 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp < 8) {
     // ======================= element-wise warpgroups =======================
+    setmaxnreg_inc<216>();
     const int wg = warp >> 2;
     const int tid = (warp & 3) * 32 + lane;  // TMEM lane = key row within the tile
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tX = tmem_base + lane_off + wg * 64;
-    const uint32_t tY = tmem_base + lane_off + 128 + wg * 64;
+    const uint32_t tX = tmem_base + lane_off + wg * 64;         // this warpgroup's half of S^T / P^T
+    const uint32_t tY = tmem_base + lane_off + 128 + wg * 64;   // ... of dP^T / dS^T
     const int key = key0 + tid;
-    // per-column statistics (L_i * log2e for threads 0-63, D_i * scale for threads 64-127) of a half
-    // tile, fetched one iteration ahead so the global-memory latency hides behind the previous tile
-    auto fetch_stat = [&](int s) -> float {
-      const int qi = (i_start + s) * 64 + (tid & 63);
-      if (s >= n || qi >= p.N) return tid < 64 ? CUDART_INF_F : 0.f;
+    // per-column statistics (L_i * log2e for threads 0-63, D_i * scale for threads 64-127) of the 64
+    // query columns this warpgroup owns, fetched one tile ahead
+    auto fetch_stat = [&](int i) -> float {
+      const int qi = (i_start + i) * 128 + wg * 64 + (tid & 63);
+      if (i >= n || qi >= p.N) return tid < 64 ? CUDART_INF_F : 0.f;
       return tid < 64 ? __ldg(p.L + vec_off + qi) * kLog2e : __ldg(p.delta + vec_off + qi) * p.scale;
     };
-    float stat_next = fetch_stat(wg);
+    float stat_next = fetch_stat(0);
     const uint64_t scale_log2_2 = pack_f32x2(p.scale_log2, p.scale_log2), scale_2 = pack_f32x2(p.scale, p.scale);
-    int it = 0;
-    for (int s = wg; s < n; s += 2, ++it) {
-      const int q0 = (i_start + s) * 64;
-      float *ld = sLD + (wg * 2 + (it & 1)) * 128;  // double-buffered per warpgroup
+    for (int i = 0; i < n; ++i) {
+      const int q0 = (i_start + i) * 128 + wg * 64;  // first query column of this warpgroup's half
+      float *ld = sLD + (wg * 2 + (i & 1)) * 128;
       ld[tid] = stat_next;
-      stat_next = fetch_stat(s + 2);
+      stat_next = fetch_stat(i + 1);
       named_bar_sync(1 + wg, 128);
-      mbar_wait(&xy_full[wg], it & 1);
+      // ---- phase 1: P^T = exp2(S^T * c - L * log2e) ----
+      mbar_wait(x_full, i & 1);
       tc_fence_after();
+      uint32_t pr[2][32];  // S^T, then P^T (fp32 bits), kept for phase 2
+      tmem_ld32(tX, pr[0]);
+      tmem_ld32(tX + 32, pr[1]);
+      tmem_wait_ld();
       const bool diag = p.causal && (q0 < key0 + 128);
+      {
+        uint32_t pk[32];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t x[32], y[32];
-        tmem_ld32(tX + c * 32, x);
-        tmem_ld32(tY + c * 32, y);
-        tmem_wait_ld();
-        uint32_t pp[16], ds[16];
-        // packed fp32x2 math: P = exp2(x*c - L*log2e), dS = P * (y*scale - D*scale)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const uint64_t l2 = *reinterpret_cast<const uint64_t *>(&ld[c * 32 + i]);
-          const uint64_t dl = *reinterpret_cast<const uint64_t *>(&ld[64 + c * 32 + i]);
-          const uint64_t e2 = fma_f32x2(pack_u32x2(x[i], x[i + 1]), scale_log2_2, neg_f32x2(l2));
-          float p0 = ex2(lo_f32(e2)), p1 = ex2(hi_f32(e2));
-          if (diag) {
-            if (key > q0 + c * 32 + i) p0 = 0.f;
-            if (key > q0 + c * 32 + i + 1) p1 = 0.f;
+          for (int e = 0; e < 32; e += 2) {
+            const uint64_t l2 = *reinterpret_cast<const uint64_t *>(&ld[c * 32 + e]);
+            const uint64_t x2 = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, neg_f32x2(l2));
+            float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
+            if (diag) {
+              if (key > q0 + c * 32 + e) p0 = 0.f;
+              if (key > q0 + c * 32 + e + 1) p1 = 0.f;
+            }
+            pr[c][e] = __float_as_uint(p0);
+            pr[c][e + 1] = __float_as_uint(p1);
+            pk[c * 16 + (e >> 1)] = pack2<IS_BF16>(p0, p1);
           }
-          const uint64_t g2 = fma_f32x2(pack_u32x2(y[i], y[i + 1]), scale_2, neg_f32x2(dl));
-          const uint64_t d2 = mul_f32x2(pack_f32x2(p0, p1), g2);
-          pp[i >> 1] = pack2<IS_BF16>(p0, p1);
-          ds[i >> 1] = pack2<IS_BF16>(lo_f32(d2), hi_f32(d2));
-        }
-        tmem_st16(tX + c * 16, pp);
-        tmem_st16(tY + c * 16, ds);
+        tmem_st32(tX, pk);
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&pds_full[wg]);
+      mbar_arrive(p_ready);
+      // ---- phase 2: dS^T = P^T o (dP^T * scale - D * scale) ----
+      mbar_wait(y_full, i & 1);
+      tc_fence_after();
+      {
+        uint32_t dk[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t y[32];
+          tmem_ld32(tY + c * 32, y);
+          tmem_wait_ld();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const uint64_t dl = *reinterpret_cast<const uint64_t *>(&ld[64 + c * 32 + e]);
+            const uint64_t g2 = fma_f32x2(pack_u32x2(y[e], y[e + 1]), scale_2, neg_f32x2(dl));
+            const uint64_t d2 = mul_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), g2);
+            dk[c * 16 + (e >> 1)] = pack2<IS_BF16>(lo_f32(d2), hi_f32(d2));
+          }
+        }
+        tmem_st32(tY, dk);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
     }
     // ------------------------------ epilogue ------------------------------
     mbar_wait(acc_full, 0);
@@ -240,82 +284,83 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (key < p.N) {
         float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          d4[i] = make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]),
-                              __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
+        for (int e = 0; e < 8; ++e)
+          d4[e] = make_float4(__uint_as_float(a[4 * e]), __uint_as_float(a[4 * e + 1]),
+                              __uint_as_float(a[4 * e + 2]), __uint_as_float(a[4 * e + 3]));
       }
     }
-  } else if (warp == kLoadWarp) {
-    // ============================ TMA producer ============================
-    if (elect_one()) {
-      prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
-      mbar_arrive_expect_tx(res_full, 2 * Cfg::kTile128);
-#pragma unroll
-      for (int c = 0; c < Cfg::kChunks; ++c) {
-        tma_load_4d(sK + c * Cfg::kChunk128, &tmK, res_full, c * 64, key0, h, b);
-        tma_load_4d(sV + c * Cfg::kChunk128, &tmV, res_full, c * 64, key0, h, b);
-      }
-      for (int s = 0; s < n; ++s) {
-        const int stage = s % Cfg::kStages;
-        mbar_wait(&st_empty[stage], ((s / Cfg::kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&st_full[stage], Cfg::kStageBytes);
-        unsigned char *dst = sStage + stage * Cfg::kStageBytes;
-        const int q0 = (i_start + s) * 64;
-#pragma unroll
-        for (int c = 0; c < Cfg::kChunks; ++c) {
-          tma_load_4d(dst + c * Cfg::kChunk64, &tmQ, &st_full[stage], c * 64, q0, h, b);
-          tma_load_4d(dst + Cfg::kTile64 + c * Cfg::kChunk64, &tmdO, &st_full[stage], c * 64, q0, h, b);
+  } else {
+    setmaxnreg_dec<64>();
+    if (warp == kLoadWarp) {
+      // ============================ TMA producer ============================
+      if (elect_one()) {
+        prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
+        mbar_arrive_expect_tx(res_full, 2 * Cfg::kTile);
+        tma_load_tile<D>(sK, &tmK, res_full, key0, h, b);
+        tma_load_tile<D>(sV, &tmV, res_full, key0, h, b);
+        for (int i = 0; i < n; ++i) {
+          const int q0 = (i_start + i) * 128;
+          const int qs = i % Cfg::kQSlots, ds = i % Cfg::kDoSlots;
+          mbar_wait(&q_empty[qs], ((i / Cfg::kQSlots) & 1) ^ 1);
+          mbar_arrive_expect_tx(&q_full[qs], Cfg::kTile);
+          tma_load_tile<D>(sQ + qs * Cfg::kTile, &tmQ, &q_full[qs], q0, h, b);
+          mbar_wait(&do_empty[ds], ((i / Cfg::kDoSlots) & 1) ^ 1);
+          mbar_arrive_expect_tx(&do_full[ds], Cfg::kTile);
+          tma_load_tile<D>(sDO + ds * Cfg::kTile, &tmdO, &do_full[ds], q0, h, b);
         }
       }
-    }
-    __syncwarp();
-  } else if (warp == kMmaWarp) {
-    // ============================= MMA issuer =============================
-    if (elect_one()) {
-      constexpr uint32_t idesc_xy = make_idesc(128, 64, IS_BF16, 0, 0);
-      constexpr uint32_t idesc_acc = make_idesc(128, D, IS_BF16, 0, 1);
-      const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV), sSt_a = smem_u32(sStage);
-      auto issue_xy = [&](int s) {
-        const int stage = s % Cfg::kStages, slot = s & 1;
-        mbar_wait(&st_full[stage], (s / Cfg::kStages) & 1);
+      __syncwarp();
+    } else if (warp == kMmaWarp) {
+      // ============================= MMA issuer =============================
+      if (elect_one()) {
+        constexpr uint32_t idesc_xy = make_idesc(128, 128, IS_BF16, 0, 0);
+        constexpr uint32_t idesc_acc = make_idesc(128, D, IS_BF16, 0, 1);
+        const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV), sQ_a = smem_u32(sQ), sDO_a = smem_u32(sDO);
+        const uint32_t tX = tmem_base, tY = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + D;
+        auto q_addr = [&](int i) { return sQ_a + (i % Cfg::kQSlots) * Cfg::kTile; };
+        auto do_addr = [&](int i) { return sDO_a + (i % Cfg::kDoSlots) * Cfg::kTile; };
+        auto issue_x = [&](int i) {  // S^T = K Q_i^T
+          mbar_wait(&q_full[i % Cfg::kQSlots], (i / Cfg::kQSlots) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk)
+            mma_ss(tX, kmajor_desc(sK_a, kk), kmajor_desc(q_addr(i), kk), idesc_xy, kk > 0);
+          tc_commit(x_full);
+        };
+        auto issue_y = [&](int i) {  // dP^T = V dO_i^T
+          mbar_wait(&do_full[i % Cfg::kDoSlots], (i / Cfg::kDoSlots) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk)
+            mma_ss(tY, kmajor_desc(sV_a, kk), kmajor_desc(do_addr(i), kk), idesc_xy, kk > 0);
+          tc_commit(y_full);
+        };
+        mbar_wait(res_full, 0);
         tc_fence_after();
-        const uint32_t q_a = sSt_a + stage * Cfg::kStageBytes, do_a = q_a + Cfg::kTile64;
+        issue_x(0);
+        issue_y(0);
+        for (int i = 0; i < n; ++i) {
+          mbar_wait(p_ready, i & 1);
+          tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // S^T = K Q^T
-          mma_ss(tmem_base + slot * 64, kmajor_desc<Cfg::kChunk128>(sK_a, kk),
-                 kmajor_desc<Cfg::kChunk64>(q_a, kk), idesc_xy, kk > 0);
+          for (int kk = 0; kk < 8; ++kk)  // dV += P^T dO_i   (K = 128 query rows)
+            mma_ts(tdV, tX + (kk >> 2) * 64 + (kk & 3) * 8, mnmajor_desc(do_addr(i), kk), idesc_acc,
+                   (i > 0 || kk > 0) ? 1u : 0u);
+          tc_commit(&do_empty[i % Cfg::kDoSlots]);
+          if (i + 1 < n) issue_x(i + 1);
+          mbar_wait(ds_ready, i & 1);
+          tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // dP^T = V dO^T
-          mma_ss(tmem_base + 128 + slot * 64, kmajor_desc<Cfg::kChunk128>(sV_a, kk),
-                 kmajor_desc<Cfg::kChunk64>(do_a, kk), idesc_xy, kk > 0);
-        tc_commit(&xy_full[slot]);
-      };
-      auto issue_acc = [&](int s) {
-        const int stage = s % Cfg::kStages, slot = s & 1;
-        mbar_wait(&pds_full[slot], (s >> 1) & 1);
-        tc_fence_after();
-        const uint32_t q_a = sSt_a + stage * Cfg::kStageBytes, do_a = q_a + Cfg::kTile64;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // dV += P^T dO   (K = 64 query rows)
-          mma_ts(tmem_base + 256, tmem_base + slot * 64 + kk * 8, mnmajor_desc<Cfg::kChunk64>(do_a, kk),
-                 idesc_acc, (s > 0 || kk > 0) ? 1u : 0u);
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // dK += dS^T Q
-          mma_ts(tmem_base + 256 + D, tmem_base + 128 + slot * 64 + kk * 8,
-                 mnmajor_desc<Cfg::kChunk64>(q_a, kk), idesc_acc, (s > 0 || kk > 0) ? 1u : 0u);
-        tc_commit(&st_empty[stage]);
-        if (s == n - 1) tc_commit(acc_full);
-      };
-      mbar_wait(res_full, 0);
-      tc_fence_after();
-      issue_xy(0);
-      if (n > 1) issue_xy(1);
-      for (int s = 0; s < n; ++s) {
-        issue_acc(s);
-        if (s + 2 < n) issue_xy(s + 2);
+          for (int kk = 0; kk < 8; ++kk)  // dK += dS^T Q_i
+            mma_ts(tdK, tY + (kk >> 2) * 64 + (kk & 3) * 8, mnmajor_desc(q_addr(i), kk), idesc_acc,
+                   (i > 0 || kk > 0) ? 1u : 0u);
+          tc_commit(&q_empty[i % Cfg::kQSlots]);
+          if (i == n - 1) tc_commit(acc_full);
+          if (i + 1 < n) issue_y(i + 1);
+        }
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
 
   tc_fence_before();
@@ -324,15 +369,19 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------
-// 3. dQ : CTA owns 2 x 128 query rows (two slots that ping-pong on the tensor core and
-//    share every streamed K/V half tile of 64 keys).
-//    TMEM: X_t = S [t*128, +64)   Y_t = dP [t*128+64, +64) (dS aliases its first 32 columns)
-//          dQ_t [256 + t*D, +D)
+// 3. dQ : CTA owns 2 x 128 query rows.  Warpgroup t owns tile t (one thread per query row, all
+//    128 key columns); the two tiles take turns on ONE S / dP buffer pair:
+//    TMEM: X = S [0,128)   Y = dP [128,256) (dS aliases its first 64 columns)
+//          dQ_0 [256,256+D)   dQ_1 [256+D,256+2D)
+//    Work items k = (s, t) in order; per item X(k) -> Y(k) -> dQ(k).  The warpgroup releases X as
+//    soon as it has copied it to registers, so the next item's S is computed under this item's
+//    exponentials:   X(0) Y(0) | xc(0)? X(1) | dS(0)? dQ(0) Y(1) | xc(1)? X(2) | dS(1)? dQ(1) Y(2) ...
 // ---------------------------------------------------------------------------
 template <int D>
 struct DqCfg : BwdCfg<D> {
-  static constexpr int kStages = D == 128 ? 3 : 4;
-  static constexpr int kSmemTiles = 4 * BwdCfg<D>::kTile128 + kStages * BwdCfg<D>::kStageBytes;
+  static constexpr int kKSlots = D == 128 ? 2 : 4;
+  static constexpr int kVSlots = D == 128 ? 1 : 2;
+  static constexpr int kSmemTiles = (4 + kKSlots + kVSlots) * BwdCfg<D>::kTile;
   static constexpr int kSmemBytes = kSmemTiles + 1024 + 256;
 };
 
@@ -345,27 +394,32 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   extern __shared__ unsigned char smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  unsigned char *sRes = smem;                          // [slot][Q tile | dO tile]
-  unsigned char *sStage = smem + 4 * Cfg::kTile128;    // [stage][K half | V half]
+  unsigned char *sRes = smem;                                   // [tile][Q | dO]
+  unsigned char *sKs = smem + 4 * Cfg::kTile;                   // [kKSlots]
+  unsigned char *sVs = sKs + Cfg::kKSlots * Cfg::kTile;         // [kVSlots]
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemTiles);
-  uint64_t *res_full = bars;       // [2]
-  uint64_t *acc_full = bars + 2;   // [2]
-  uint64_t *xy_full = bars + 4;    // [2]
-  uint64_t *ds_full = bars + 6;    // [2]
-  uint64_t *st_full = bars + 8;
-  uint64_t *st_empty = bars + 8 + Cfg::kStages;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 8 + 2 * Cfg::kStages);
+  uint64_t *res_full = bars;        // [2]
+  uint64_t *acc_full = bars + 2;    // [2]
+  uint64_t *x_full = bars + 4;      // [2] S of tile t ready
+  uint64_t *y_full = bars + 6;      // [2] dP of tile t ready
+  uint64_t *x_taken = bars + 8;     // [2] warpgroup t has copied S to registers
+  uint64_t *ds_ready = bars + 10;   // [2] warpgroup t has stored dS
+  uint64_t *k_full = bars + 12;
+  uint64_t *k_empty = k_full + Cfg::kKSlots;
+  uint64_t *v_full = k_empty + Cfg::kKSlots;
+  uint64_t *v_empty = v_full + Cfg::kVSlots;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(v_empty + Cfg::kVSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.y, b = blockIdx.z;
   const int qb = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heaviest first
   const int q_row0 = qb * 256;
-  const int n_half_all = (p.N + 63) / 64;
+  const int n_tiles_all = (p.N + 127) / 128;
   int n_t[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int r0 = q_row0 + t * 128;
-    n_t[t] = r0 >= p.N ? 0 : (p.causal ? min(n_half_all, r0 / 64 + 2) : n_half_all);
+    n_t[t] = r0 >= p.N ? 0 : (p.causal ? min(n_tiles_all, r0 / 128 + 1) : n_tiles_all);
   }
   const int nmax = max(n_t[0], n_t[1]);
   const int64_t head_off = (int64_t)b * p.batch_stride + (int64_t)h * p.head_stride;
@@ -374,9 +428,11 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&res_full[i], 1); mbar_init(&acc_full[i], 1);
-      mbar_init(&xy_full[i], 1); mbar_init(&ds_full[i], 128);
+      mbar_init(&x_full[i], 1); mbar_init(&y_full[i], 1);
+      mbar_init(&x_taken[i], 128); mbar_init(&ds_ready[i], 128);
     }
-    for (int i = 0; i < Cfg::kStages; ++i) { mbar_init(&st_full[i], 1); mbar_init(&st_empty[i], 1); }
+    for (int i = 0; i < Cfg::kKSlots; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < Cfg::kVSlots; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     fence_barrier_init();
   }
   if (warp == kMmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -387,11 +443,12 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
   if (warp < 8) {
     // ======================= element-wise warpgroups =======================
+    setmaxnreg_inc<216>();
     const int t = warp >> 2;
     const int tid = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tX = tmem_base + lane_off + t * 128;
-    const uint32_t tY = tX + 64;
+    const uint32_t tX = tmem_base + lane_off;
+    const uint32_t tY = tmem_base + lane_off + 128;
     const int row = q_row0 + t * 128 + tid;
     const int nt = n_t[t];
     const float l2 = row < p.N ? __ldg(p.L + vec_off + row) * kLog2e : CUDART_INF_F;
@@ -399,34 +456,49 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint64_t scale_log2_2 = pack_f32x2(p.scale_log2, p.scale_log2), scale_2 = pack_f32x2(p.scale, p.scale);
     const uint64_t neg_l2_2 = pack_f32x2(-l2, -l2), neg_dls_2 = pack_f32x2(-dl * p.scale, -dl * p.scale);
     for (int s = 0; s < nt; ++s) {
-      mbar_wait(&xy_full[t], s & 1);
+      // ---- phase 1: copy S out (frees X for the other tile), P = exp2(S * c - L * log2e) ----
+      mbar_wait(&x_full[t], s & 1);
       tc_fence_after();
-      const int k0 = s * 64;
-      const bool diag = p.causal && (k0 + 63 > q_row0 + t * 128);
+      uint32_t pr[4][32];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t x[32], y[32];
-        tmem_ld32(tX + c * 32, x);
+      for (int c = 0; c < 4; ++c) tmem_ld32(tX + c * 32, pr[c]);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&x_taken[t]);
+      const int k0 = s * 128;
+      const bool diag = p.causal && (s == nt - 1);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          const uint64_t x2 = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, neg_l2_2);
+          float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
+          if (diag) {
+            if (k0 + c * 32 + e > row) p0 = 0.f;
+            if (k0 + c * 32 + e + 1 > row) p1 = 0.f;
+          }
+          pr[c][e] = __float_as_uint(p0);
+          pr[c][e + 1] = __float_as_uint(p1);
+        }
+      // ---- phase 2: dS = P o (dP * scale - D * scale), 16-bit, over the first half of Y ----
+      mbar_wait(&y_full[t], s & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t y[32], dk[16];
         tmem_ld32(tY + c * 32, y);
         tmem_wait_ld();
-        uint32_t ds[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          const uint64_t e2 = fma_f32x2(pack_u32x2(x[i], x[i + 1]), scale_log2_2, neg_l2_2);
-          float p0 = ex2(lo_f32(e2)), p1 = ex2(hi_f32(e2));
-          if (diag) {
-            if (k0 + c * 32 + i > row) p0 = 0.f;
-            if (k0 + c * 32 + i + 1 > row) p1 = 0.f;
-          }
-          const uint64_t g2 = fma_f32x2(pack_u32x2(y[i], y[i + 1]), scale_2, neg_dls_2);
-          const uint64_t d2 = mul_f32x2(pack_f32x2(p0, p1), g2);
-          ds[i >> 1] = pack2<IS_BF16>(lo_f32(d2), hi_f32(d2));
+        for (int e = 0; e < 32; e += 2) {
+          const uint64_t g2 = fma_f32x2(pack_u32x2(y[e], y[e + 1]), scale_2, neg_dls_2);
+          const uint64_t d2 = mul_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), g2);
+          dk[e >> 1] = pack2<IS_BF16>(lo_f32(d2), hi_f32(d2));
         }
-        tmem_st16(tY + c * 16, ds);
+        tmem_st16(tY + c * 16, dk);  // columns [16c, 16c+16) were read in chunk <= c
       }
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&ds_full[t]);
+      mbar_arrive(&ds_ready[t]);
     }
     if (nt > 0) {
       mbar_wait(&acc_full[t], 0);
@@ -441,90 +513,95 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (row < p.N) {
           float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            d4[i] = make_float4(__uint_as_float(a[4 * i]), __uint_as_float(a[4 * i + 1]),
-                                __uint_as_float(a[4 * i + 2]), __uint_as_float(a[4 * i + 3]));
+          for (int e = 0; e < 8; ++e)
+            d4[e] = make_float4(__uint_as_float(a[4 * e]), __uint_as_float(a[4 * e + 1]),
+                                __uint_as_float(a[4 * e + 2]), __uint_as_float(a[4 * e + 3]));
         }
       }
     }
-  } else if (warp == kLoadWarp) {
-    if (elect_one()) {
-      prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
+  } else {
+    setmaxnreg_dec<64>();
+    if (warp == kLoadWarp) {
+      if (elect_one()) {
+        prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
 #pragma unroll
-      for (int t = 0; t < 2; ++t)
-        if (n_t[t] > 0) {
-          mbar_arrive_expect_tx(&res_full[t], 2 * Cfg::kTile128);
-          unsigned char *dst = sRes + t * 2 * Cfg::kTile128;
-#pragma unroll
-          for (int c = 0; c < Cfg::kChunks; ++c) {
-            tma_load_4d(dst + c * Cfg::kChunk128, &tmQ, &res_full[t], c * 64, q_row0 + t * 128, h, b);
-            tma_load_4d(dst + Cfg::kTile128 + c * Cfg::kChunk128, &tmdO, &res_full[t], c * 64, q_row0 + t * 128, h, b);
+        for (int t = 0; t < 2; ++t)
+          if (n_t[t] > 0) {
+            mbar_arrive_expect_tx(&res_full[t], 2 * Cfg::kTile);
+            tma_load_tile<D>(sRes + t * 2 * Cfg::kTile, &tmQ, &res_full[t], q_row0 + t * 128, h, b);
+            tma_load_tile<D>(sRes + t * 2 * Cfg::kTile + Cfg::kTile, &tmdO, &res_full[t], q_row0 + t * 128, h, b);
           }
-        }
-      for (int s = 0; s < nmax; ++s) {
-        const int stage = s % Cfg::kStages;
-        mbar_wait(&st_empty[stage], ((s / Cfg::kStages) & 1) ^ 1);
-        mbar_arrive_expect_tx(&st_full[stage], Cfg::kStageBytes);
-        unsigned char *dst = sStage + stage * Cfg::kStageBytes;
-#pragma unroll
-        for (int c = 0; c < Cfg::kChunks; ++c) {
-          tma_load_4d(dst + c * Cfg::kChunk64, &tmK, &st_full[stage], c * 64, s * 64, h, b);
-          tma_load_4d(dst + Cfg::kTile64 + c * Cfg::kChunk64, &tmV, &st_full[stage], c * 64, s * 64, h, b);
+        for (int s = 0; s < nmax; ++s) {
+          const int ks = s % Cfg::kKSlots, vs = s % Cfg::kVSlots;
+          mbar_wait(&k_empty[ks], ((s / Cfg::kKSlots) & 1) ^ 1);
+          mbar_arrive_expect_tx(&k_full[ks], Cfg::kTile);
+          tma_load_tile<D>(sKs + ks * Cfg::kTile, &tmK, &k_full[ks], s * 128, h, b);
+          mbar_wait(&v_empty[vs], ((s / Cfg::kVSlots) & 1) ^ 1);
+          mbar_arrive_expect_tx(&v_full[vs], Cfg::kTile);
+          tma_load_tile<D>(sVs + vs * Cfg::kTile, &tmV, &v_full[vs], s * 128, h, b);
         }
       }
-    }
-    __syncwarp();
-  } else if (warp == kMmaWarp) {
-    if (elect_one()) {
-      constexpr uint32_t idesc_xy = make_idesc(128, 64, IS_BF16, 0, 0);
-      constexpr uint32_t idesc_acc = make_idesc(128, D, IS_BF16, 0, 1);
-      const uint32_t sRes_a = smem_u32(sRes), sSt_a = smem_u32(sStage);
-      auto wait_stage = [&](int s) {
-        mbar_wait(&st_full[s % Cfg::kStages], (s / Cfg::kStages) & 1);
-        tc_fence_after();
-      };
-      auto issue_xy = [&](int t, int s) {
-        const uint32_t q_a = sRes_a + t * 2 * Cfg::kTile128, do_a = q_a + Cfg::kTile128;
-        const uint32_t k_a = sSt_a + (s % Cfg::kStages) * Cfg::kStageBytes, v_a = k_a + Cfg::kTile64;
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // S = Q K^T
-          mma_ss(tmem_base + t * 128, kmajor_desc<Cfg::kChunk128>(q_a, kk),
-                 kmajor_desc<Cfg::kChunk64>(k_a, kk), idesc_xy, kk > 0);
-#pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk)  // dP = dO V^T
-          mma_ss(tmem_base + t * 128 + 64, kmajor_desc<Cfg::kChunk128>(do_a, kk),
-                 kmajor_desc<Cfg::kChunk64>(v_a, kk), idesc_xy, kk > 0);
-        tc_commit(&xy_full[t]);
-      };
-      auto issue_acc = [&](int t, int s) {
-        mbar_wait(&ds_full[t], s & 1);
-        tc_fence_after();
-        const uint32_t k_a = sSt_a + (s % Cfg::kStages) * Cfg::kStageBytes;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk)  // dQ += dS K   (K = 64 keys)
-          mma_ts(tmem_base + 256 + t * D, tmem_base + t * 128 + 64 + kk * 8,
-                 mnmajor_desc<Cfg::kChunk64>(k_a, kk), idesc_acc, (s > 0 || kk > 0) ? 1u : 0u);
-        if (s == n_t[t] - 1) tc_commit(&acc_full[t]);
-      };
-      wait_stage(0);
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-        if (n_t[t] > 0) {
-          mbar_wait(&res_full[t], 0);
+      __syncwarp();
+    } else if (warp == kMmaWarp) {
+      if (elect_one()) {
+        constexpr uint32_t idesc_xy = make_idesc(128, 128, IS_BF16, 0, 0);
+        constexpr uint32_t idesc_acc = make_idesc(128, D, IS_BF16, 0, 1);
+        const uint32_t sRes_a = smem_u32(sRes), sK_a = smem_u32(sKs), sV_a = smem_u32(sVs);
+        const uint32_t tX = tmem_base, tY = tmem_base + 128;
+        auto k_addr = [&](int s) { return sK_a + (s % Cfg::kKSlots) * Cfg::kTile; };
+        auto v_addr = [&](int s) { return sV_a + (s % Cfg::kVSlots) * Cfg::kTile; };
+        // item k -> (s, t); items run s-major over the tiles that still have work
+        auto item_s = [&](int k) { return k < 2 * min(n_t[0], n_t[1]) ? k >> 1 : k - min(n_t[0], n_t[1]); };
+        auto item_t = [&](int k) { return k < 2 * min(n_t[0], n_t[1]) ? k & 1 : (n_t[0] > n_t[1] ? 0 : 1); };
+        const int n_items = n_t[0] + n_t[1];
+        int k_waited = -1, v_waited = -1;  // highest s whose K / V tile is known to have landed
+        bool res_waited[2] = {false, false};
+        auto issue_x = [&](int k) {  // S = Q_t K_s^T
+          const int s = item_s(k), t = item_t(k);
+          if (!res_waited[t]) { mbar_wait(&res_full[t], 0); res_waited[t] = true; }
+          if (s > k_waited) { mbar_wait(&k_full[s % Cfg::kKSlots], (s / Cfg::kKSlots) & 1); k_waited = s; }
           tc_fence_after();
-          issue_xy(t, 0);
-        }
-      for (int s = 0; s < nmax; ++s) {
-        if (s + 1 < nmax) wait_stage(s + 1);
+          const uint32_t q_a = sRes_a + t * 2 * Cfg::kTile;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          if (s < n_t[t]) issue_acc(t, s);
-          if (s + 1 < n_t[t]) issue_xy(t, s + 1);
+          for (int kk = 0; kk < D / 16; ++kk)
+            mma_ss(tX, kmajor_desc(q_a, kk), kmajor_desc(k_addr(s), kk), idesc_xy, kk > 0);
+          tc_commit(&x_full[t]);
+        };
+        auto issue_y = [&](int k) {  // dP = dO_t V_s^T
+          const int s = item_s(k), t = item_t(k);
+          if (s > v_waited) { mbar_wait(&v_full[s % Cfg::kVSlots], (s / Cfg::kVSlots) & 1); v_waited = s; }
+          tc_fence_after();
+          const uint32_t do_a = sRes_a + t * 2 * Cfg::kTile + Cfg::kTile;
+#pragma unroll
+          for (int kk = 0; kk < D / 16; ++kk)
+            mma_ss(tY, kmajor_desc(do_a, kk), kmajor_desc(v_addr(s), kk), idesc_xy, kk > 0);
+          tc_commit(&y_full[t]);
+          // last use of V_s: release its slot once this MMA has completed
+          if (k + 1 >= n_items || item_s(k + 1) != s) tc_commit(&v_empty[s % Cfg::kVSlots]);
+        };
+        if (n_items > 0) {
+          issue_x(0);
+          issue_y(0);
         }
-        tc_commit(&st_empty[s % Cfg::kStages]);
+        for (int k = 0; k < n_items; ++k) {
+          const int s = item_s(k), t = item_t(k);
+          if (k + 1 < n_items) {
+            mbar_wait(&x_taken[t], s & 1);  // X is free again
+            issue_x(k + 1);
+          }
+          mbar_wait(&ds_ready[t], s & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)  // dQ_t += dS K_s   (K = 128 keys)
+            mma_ts(tmem_base + 256 + t * D, tY + kk * 8, mnmajor_desc(k_addr(s), kk), idesc_acc,
+                   (s > 0 || kk > 0) ? 1u : 0u);
+          if (s == n_t[t] - 1) tc_commit(&acc_full[t]);
+          if (k + 1 >= n_items || item_s(k + 1) != s) tc_commit(&k_empty[s % Cfg::kKSlots]);
+          if (k + 1 < n_items) issue_y(k + 1);
+        }
       }
+      __syncwarp();
     }
-    __syncwarp();
   }
 
   tc_fence_before();
@@ -533,8 +610,8 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 }
 
 template <int D, int IS_BF16>
-int launch_bwd_impl(const void *O, const void *dO, float *delta, const CUtensorMap *maps64,
-                    const CUtensorMap *maps128, const BwdParams &p, int B, cudaStream_t stream) {
+int launch_bwd_impl(const void *O, const void *dO, float *delta, const CUtensorMap *maps, const BwdParams &p, int B,
+                    cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     FA_CUDA_CHECK(cudaFuncSetAttribute(bwd_dkdv_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -543,16 +620,16 @@ int launch_bwd_impl(const void *O, const void *dO, float *delta, const CUtensorM
                                        DqCfg<D>::kSmemBytes));
     configured = true;
   }
-  // maps: [0] Q, [1] K, [2] V, [3] dO
+  // maps: [0] Q, [1] K, [2] V, [3] dO, all with 128-row boxes
   bwd_delta_kernel<D, IS_BF16><<<dim3((p.N + 7) / 8, p.H, B), 256, 0, stream>>>(
       reinterpret_cast<const uint16_t *>(O), reinterpret_cast<const uint16_t *>(dO), delta, p.N, p.H,
       p.batch_stride, p.head_stride);
   FA_CUDA_CHECK(cudaGetLastError());
   bwd_dkdv_kernel<D, IS_BF16><<<dim3((p.N + 127) / 128, p.H, B), kBwdThreads, DkdvCfg<D>::kSmemBytes, stream>>>(
-      maps64[0], maps128[1], maps128[2], maps64[3], p);
+      maps[0], maps[1], maps[2], maps[3], p);
   FA_CUDA_CHECK(cudaGetLastError());
   bwd_dq_kernel<D, IS_BF16><<<dim3((p.N + 255) / 256, p.H, B), kBwdThreads, DqCfg<D>::kSmemBytes, stream>>>(
-      maps128[0], maps64[1], maps64[2], maps128[3], p);
+      maps[0], maps[1], maps[2], maps[3], p);
   FA_CUDA_CHECK(cudaGetLastError());
   count_launch(3);
   return FA_OK;
@@ -584,13 +661,11 @@ int launch_bwd_tc(const void *Q, const void *K, const void *V, const void *O, co
                      "backward workspace too small: need %zu bytes (fa_workspace_bytes_backward; contiguous "
                      "[B,H,N,D] layout assumed), got %zu",
                      need, workspace_bytes);
-  CUtensorMap m64[4], m128[4];
+  CUtensorMap maps[4];
   const void *ptrs[4] = {Q, K, V, dO};
   int rc;
-  for (int i = 0; i < 4; ++i) {
-    if ((rc = make_tensor_map_bhnd(&m64[i], ptrs[i], dtype, N, D, H, B, head_stride, batch_stride, 64)) != FA_OK) return rc;
-    if ((rc = make_tensor_map_bhnd(&m128[i], ptrs[i], dtype, N, D, H, B, head_stride, batch_stride, 128)) != FA_OK) return rc;
-  }
+  for (int i = 0; i < 4; ++i)
+    if ((rc = make_tensor_map_bhnd(&maps[i], ptrs[i], dtype, N, D, H, B, head_stride, batch_stride, 128)) != FA_OK) return rc;
   BwdParams p;
   p.L = L;
   p.delta = reinterpret_cast<const float *>(workspace);
@@ -603,10 +678,10 @@ int launch_bwd_tc(const void *Q, const void *K, const void *V, const void *O, co
   p.causal = is_causal ? 1 : 0;
   float *delta = reinterpret_cast<float *>(workspace);
   if (D == 64)
-    return dtype == FA_DTYPE_BF16 ? launch_bwd_impl<64, 1>(O, dO, delta, m64, m128, p, B, stream)
-                                  : launch_bwd_impl<64, 0>(O, dO, delta, m64, m128, p, B, stream);
-  return dtype == FA_DTYPE_BF16 ? launch_bwd_impl<128, 1>(O, dO, delta, m64, m128, p, B, stream)
-                                : launch_bwd_impl<128, 0>(O, dO, delta, m64, m128, p, B, stream);
+    return dtype == FA_DTYPE_BF16 ? launch_bwd_impl<64, 1>(O, dO, delta, maps, p, B, stream)
+                                  : launch_bwd_impl<64, 0>(O, dO, delta, maps, p, B, stream);
+  return dtype == FA_DTYPE_BF16 ? launch_bwd_impl<128, 1>(O, dO, delta, maps, p, B, stream)
+                                : launch_bwd_impl<128, 0>(O, dO, delta, maps, p, B, stream);
 }
 
 }  // namespace fa
