@@ -23,6 +23,8 @@ void count_launch(int n) { g_launches += n; }
 
 }  // namespace fa
 
+namespace fa { long long *g_fwd_prof = nullptr; }
+
 using namespace fa;
 
 extern "C" {
@@ -31,6 +33,10 @@ const char *fa_last_error(void) { return g_err; }
 int fa_version(void) { return 100; }
 long fa_launch_count(void) { return g_launches; }
 void fa_reset_launch_count(void) { g_launches = 0; }
+
+// Development aid (not in the public header): device buffer of >= 32 int64 that the backward dK/dV
+// kernel fills with phase timings of one CTA; pass NULL to switch it off.
+void fa_debug_set_prof_buffer(long long *dev) { g_fwd_prof = dev; }
 
 int fa_device_count(void) {
   int n = 0;

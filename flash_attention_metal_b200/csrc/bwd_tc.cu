@@ -44,6 +44,7 @@ constexpr int kBwdThreads = 384;
 constexpr int kMmaWarp = 8;
 constexpr int kLoadWarp = 9;
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr bool kEmulateHalfExp = false;  // dK/dV phase 1: measured neutral (the GPU is power-capped at this load), kept off
 
 struct BwdParams {
   const float *L;      // [B, H, N] log-sum-exp of the scaled scores (natural log)
@@ -53,6 +54,7 @@ struct BwdParams {
   float scale, scale_log2;
   int64_t batch_stride, head_stride;  // elements
   int causal;
+  long long *prof;  // optional phase-timing buffer (development aid), normally null
 };
 
 // ---------------------------------------------------------------------------
@@ -202,15 +204,17 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t tX = tmem_base + lane_off + wg * 64;         // this warpgroup's half of S^T / P^T
     const uint32_t tY = tmem_base + lane_off + 128 + wg * 64;   // ... of dP^T / dS^T
     const int key = key0 + tid;
-    // per-column statistics (L_i * log2e for threads 0-63, D_i * scale for threads 64-127) of the 64
+    // per-column statistics (-L_i * log2e for threads 0-63, -D_i * scale for threads 64-127) of the 64
     // query columns this warpgroup owns, fetched one tile ahead
     auto fetch_stat = [&](int i) -> float {
       const int qi = (i_start + i) * 128 + wg * 64 + (tid & 63);
-      if (i >= n || qi >= p.N) return tid < 64 ? CUDART_INF_F : 0.f;
-      return tid < 64 ? __ldg(p.L + vec_off + qi) * kLog2e : __ldg(p.delta + vec_off + qi) * p.scale;
+      if (i >= n || qi >= p.N) return tid < 64 ? -CUDART_INF_F : 0.f;
+      return tid < 64 ? -__ldg(p.L + vec_off + qi) * kLog2e : -__ldg(p.delta + vec_off + qi) * p.scale;
     };
     float stat_next = fetch_stat(0);
     const uint64_t scale_log2_2 = pack_f32x2(p.scale_log2, p.scale_log2), scale_2 = pack_f32x2(p.scale, p.scale);
+    const bool prof = p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
+    long long tw_x = 0, t_p1 = 0, tw_y = 0, t_p2 = 0, t_begin = prof ? clock64() : 0;
     for (int i = 0; i < n; ++i) {
       const int q0 = (i_start + i) * 128 + wg * 64;  // first query column of this warpgroup's half
       float *ld = sLD + (wg * 2 + (i & 1)) * 128;
@@ -218,37 +222,62 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       stat_next = fetch_stat(i + 1);
       named_bar_sync(1 + wg, 128);
       // ---- phase 1: P^T = exp2(S^T * c - L * log2e) ----
+      long long c0 = prof ? clock64() : 0;
       mbar_wait(x_full, i & 1);
+      long long c1 = prof ? clock64() : 0;
       tc_fence_after();
       uint32_t pr[2][32];  // S^T, then P^T (fp32 bits), kept for phase 2
       tmem_ld32(tX, pr[0]);
       tmem_ld32(tX + 32, pr[1]);
       tmem_wait_ld();
       const bool diag = p.causal && (q0 < key0 + 128);
+      const uint32_t ld_s = smem_u32(ld);
       {
         uint32_t pk[32];
+        if (!diag) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+          for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const uint64_t l2 = *reinterpret_cast<const uint64_t *>(&ld[c * 32 + e]);
-            const uint64_t x2 = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, neg_f32x2(l2));
-            float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
-            if (diag) {
+            for (int e = 0; e < 32; e += 4) {
+              uint64_t la, lb;  // -L*log2e of four consecutive query columns
+              lds_v2b64(ld_s + (c * 32 + e) * 4, la, lb);
+              const uint64_t xa = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, la);
+              const uint64_t xb = fma_f32x2(pack_u32x2(pr[c][e + 2], pr[c][e + 3]), scale_log2_2, lb);
+              // both warpgroups run this phase at the same time, two warps per scheduler sharing
+              // one MUFU unit: every second pair goes to the FMA pipe instead
+              const float p0 = ex2(lo_f32(xa)), p1 = ex2(hi_f32(xa));
+              const uint64_t pb = kEmulateHalfExp ? exp2_emulated_x2(xb) : pack_f32x2(ex2(lo_f32(xb)), ex2(hi_f32(xb)));
+              const float p2 = lo_f32(pb), p3 = hi_f32(pb);
+              pr[c][e] = __float_as_uint(p0); pr[c][e + 1] = __float_as_uint(p1);
+              pr[c][e + 2] = __float_as_uint(p2); pr[c][e + 3] = __float_as_uint(p3);
+              pk[c * 16 + (e >> 1)] = pack2<IS_BF16>(p0, p1);
+              pk[c * 16 + (e >> 1) + 1] = pack2<IS_BF16>(p2, p3);
+            }
+        } else {  // diagonal tile: keys after the query are masked
+#pragma unroll
+          for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              uint64_t la, lb;
+              lds_v2b64(ld_s + (c * 32 + (e & ~3)) * 4, la, lb);
+              const uint64_t x2 = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, (e & 2) ? lb : la);
+              float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
               if (key > q0 + c * 32 + e) p0 = 0.f;
               if (key > q0 + c * 32 + e + 1) p1 = 0.f;
+              pr[c][e] = __float_as_uint(p0);
+              pr[c][e + 1] = __float_as_uint(p1);
+              pk[c * 16 + (e >> 1)] = pack2<IS_BF16>(p0, p1);
             }
-            pr[c][e] = __float_as_uint(p0);
-            pr[c][e + 1] = __float_as_uint(p1);
-            pk[c * 16 + (e >> 1)] = pack2<IS_BF16>(p0, p1);
-          }
+        }
         tmem_st32(tX, pk);
       }
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(p_ready);
       // ---- phase 2: dS^T = P^T o (dP^T * scale - D * scale) ----
+      long long c2 = prof ? clock64() : 0;
       mbar_wait(y_full, i & 1);
+      long long c3 = prof ? clock64() : 0;
       tc_fence_after();
       {
         uint32_t dk[32];
@@ -258,11 +287,15 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           tmem_ld32(tY + c * 32, y);
           tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const uint64_t dl = *reinterpret_cast<const uint64_t *>(&ld[64 + c * 32 + e]);
-            const uint64_t g2 = fma_f32x2(pack_u32x2(y[e], y[e + 1]), scale_2, neg_f32x2(dl));
-            const uint64_t d2 = mul_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), g2);
-            dk[c * 16 + (e >> 1)] = pack2<IS_BF16>(lo_f32(d2), hi_f32(d2));
+          for (int e = 0; e < 32; e += 4) {
+            uint64_t da, db;  // -D*scale of four consecutive query columns
+            lds_v2b64(ld_s + (64 + c * 32 + e) * 4, da, db);
+            const uint64_t ga = fma_f32x2(pack_u32x2(y[e], y[e + 1]), scale_2, da);
+            const uint64_t gb = fma_f32x2(pack_u32x2(y[e + 2], y[e + 3]), scale_2, db);
+            const uint64_t d2a = mul_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), ga);
+            const uint64_t d2b = mul_f32x2(pack_u32x2(pr[c][e + 2], pr[c][e + 3]), gb);
+            dk[c * 16 + (e >> 1)] = pack2<IS_BF16>(lo_f32(d2a), hi_f32(d2a));
+            dk[c * 16 + (e >> 1) + 1] = pack2<IS_BF16>(lo_f32(d2b), hi_f32(d2b));
           }
         }
         tmem_st32(tY, dk);
@@ -270,6 +303,11 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_wait_st();
       tc_fence_before();
       mbar_arrive(ds_ready);
+      if (prof) { tw_x += c1 - c0; t_p1 += c2 - c1; tw_y += c3 - c2; t_p2 += clock64() - c3; }
+    }
+    if (prof) {
+      long long *o = p.prof + wg * 8;
+      o[0] = n; o[1] = tw_x; o[2] = t_p1; o[3] = tw_y; o[4] = t_p2; o[5] = clock64() - t_begin;
     }
     // ------------------------------ epilogue ------------------------------
     mbar_wait(acc_full, 0);
@@ -335,12 +373,16 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mma_ss(tY, kmajor_desc(sV_a, kk), kmajor_desc(do_addr(i), kk), idesc_xy, kk > 0);
           tc_commit(y_full);
         };
+        const bool mprof = p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
+        long long mw_p = 0, mw_ds = 0, m_begin = mprof ? clock64() : 0;
         mbar_wait(res_full, 0);
         tc_fence_after();
         issue_x(0);
         issue_y(0);
         for (int i = 0; i < n; ++i) {
+          long long w0 = mprof ? clock64() : 0;
           mbar_wait(p_ready, i & 1);
+          if (mprof) mw_p += clock64() - w0;
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // dV += P^T dO_i   (K = 128 query rows)
@@ -348,7 +390,9 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                    (i > 0 || kk > 0) ? 1u : 0u);
           tc_commit(&do_empty[i % Cfg::kDoSlots]);
           if (i + 1 < n) issue_x(i + 1);
+          w0 = mprof ? clock64() : 0;
           mbar_wait(ds_ready, i & 1);
+          if (mprof) mw_ds += clock64() - w0;
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)  // dK += dS^T Q_i
@@ -358,6 +402,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (i == n - 1) tc_commit(acc_full);
           if (i + 1 < n) issue_y(i + 1);
         }
+        if (mprof) { p.prof[16] = mw_p; p.prof[17] = mw_ds; p.prof[18] = clock64() - m_begin; }
       }
       __syncwarp();
     }
@@ -467,19 +512,28 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       mbar_arrive(&x_taken[t]);
       const int k0 = s * 128;
       const bool diag = p.causal && (s == nt - 1);
+      if (!diag) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          const uint64_t x2 = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, neg_l2_2);
-          float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
-          if (diag) {
+          for (int e = 0; e < 32; e += 2) {
+            const uint64_t x2 = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, neg_l2_2);
+            pr[c][e] = __float_as_uint(ex2(lo_f32(x2)));
+            pr[c][e + 1] = __float_as_uint(ex2(hi_f32(x2)));
+          }
+      } else {  // diagonal tile: keys after the query are masked
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const uint64_t x2 = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, neg_l2_2);
+            float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
             if (k0 + c * 32 + e > row) p0 = 0.f;
             if (k0 + c * 32 + e + 1 > row) p1 = 0.f;
+            pr[c][e] = __float_as_uint(p0);
+            pr[c][e + 1] = __float_as_uint(p1);
           }
-          pr[c][e] = __float_as_uint(p0);
-          pr[c][e + 1] = __float_as_uint(p1);
-        }
+      }
       // ---- phase 2: dS = P o (dP * scale - D * scale), 16-bit, over the first half of Y ----
       mbar_wait(&y_full[t], s & 1);
       tc_fence_after();
@@ -676,6 +730,7 @@ int launch_bwd_tc(const void *Q, const void *K, const void *V, const void *O, co
   p.batch_stride = batch_stride;
   p.head_stride = head_stride;
   p.causal = is_causal ? 1 : 0;
+  p.prof = g_fwd_prof;
   float *delta = reinterpret_cast<float *>(workspace);
   if (D == 64)
     return dtype == FA_DTYPE_BF16 ? launch_bwd_impl<64, 1>(O, dO, delta, maps, p, B, stream)

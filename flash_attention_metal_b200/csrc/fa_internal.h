@@ -42,6 +42,8 @@ int launch_fwd_tc_rect(const void *Q, const void *K, const void *V, void *O, flo
                        int64_t kv_batch_stride, int64_t kv_head_stride, int is_causal, int B, int H,
                        int dtype, cudaStream_t stream);
 
+extern long long *g_fwd_prof;  // development aid: phase-timing buffer, see fa_debug_set_prof_buffer
+
 // backward (bwd_tc.cu)
 int launch_bwd_tc(const void *Q, const void *K, const void *V, const void *O, const void *dO,
                   const float *L, float *dQ, float *dK, float *dV, int N, int D, float scale,
