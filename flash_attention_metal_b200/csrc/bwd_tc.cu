@@ -50,10 +50,12 @@ struct BwdParams {
   const float *L;      // [B, H, N] log-sum-exp of the scaled scores (natural log)
   const float *delta;  // [B, H, N] D_i (workspace)
   float *dQ, *dK, *dV;
-  int N, H;
+  int Nq, Nk, H;      // query rows / keys (equal except for ring-attention blocks)
   float scale, scale_log2;
-  int64_t batch_stride, head_stride;  // elements
-  int causal;
+  int64_t batch_stride, head_stride;        // elements, of Q / O / dO / dQ (and L, delta via / D)
+  int64_t kv_batch_stride, kv_head_stride;  // elements, of K / V / dK / dV
+  int causal;         // requires Nq == Nk
+  int acc_dq;         // dQ += instead of dQ = (ring attention accumulates over K/V chunks)
   long long *prof;  // optional phase-timing buffer (development aid), normally null
 };
 
@@ -172,11 +174,11 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int key0 = j * 128;
-  const int n_tiles_all = (p.N + 127) / 128;
+  const int n_tiles_all = (p.Nq + 127) / 128;
   const int i_start = p.causal ? j : 0;    // first query tile that sees these keys
-  const int n = n_tiles_all - i_start;     // >= 1 because key0 < N
-  const int64_t head_off = (int64_t)b * p.batch_stride + (int64_t)h * p.head_stride;
-  const int64_t vec_off = head_off / D;
+  const int n = n_tiles_all - i_start;     // >= 1 because key0 < Nk (and Nq == Nk when causal)
+  const int64_t kv_off = (int64_t)b * p.kv_batch_stride + (int64_t)h * p.kv_head_stride;
+  const int64_t vec_off = ((int64_t)b * p.batch_stride + (int64_t)h * p.head_stride) / D;
 
   if (threadIdx.x == 0) {
     mbar_init(res_full, 1);
@@ -208,7 +210,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // query columns this warpgroup owns, fetched one tile ahead
     auto fetch_stat = [&](int i) -> float {
       const int qi = (i_start + i) * 128 + wg * 64 + (tid & 63);
-      if (i >= n || qi >= p.N) return tid < 64 ? -CUDART_INF_F : 0.f;
+      if (i >= n || qi >= p.Nq) return tid < 64 ? -CUDART_INF_F : 0.f;
       return tid < 64 ? -__ldg(p.L + vec_off + qi) * kLog2e : -__ldg(p.delta + vec_off + qi) * p.scale;
     };
     float stat_next = fetch_stat(0);
@@ -313,13 +315,13 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_wait(acc_full, 0);
     tc_fence_after();
     const uint32_t tAcc = tmem_base + lane_off + 256 + wg * D;  // wg 0 -> dV, wg 1 -> dK
-    float *dst = (wg == 0 ? p.dV : p.dK) + head_off + (int64_t)key * D;
+    float *dst = (wg == 0 ? p.dV : p.dK) + kv_off + (int64_t)key * D;
 #pragma unroll
     for (int c = 0; c < D / 32; ++c) {
       uint32_t a[32];
       tmem_ld32(tAcc + c * 32, a);
       tmem_wait_ld();
-      if (key < p.N) {
+      if (key < p.Nk) {
         float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
 #pragma unroll
         for (int e = 0; e < 8; ++e)
@@ -459,12 +461,12 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int h = blockIdx.y, b = blockIdx.z;
   const int qb = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heaviest first
   const int q_row0 = qb * 256;
-  const int n_tiles_all = (p.N + 127) / 128;
+  const int n_tiles_all = (p.Nk + 127) / 128;
   int n_t[2];
 #pragma unroll
   for (int t = 0; t < 2; ++t) {
     const int r0 = q_row0 + t * 128;
-    n_t[t] = r0 >= p.N ? 0 : (p.causal ? min(n_tiles_all, r0 / 128 + 1) : n_tiles_all);
+    n_t[t] = r0 >= p.Nq ? 0 : (p.causal ? min(n_tiles_all, r0 / 128 + 1) : n_tiles_all);
   }
   const int nmax = max(n_t[0], n_t[1]);
   const int64_t head_off = (int64_t)b * p.batch_stride + (int64_t)h * p.head_stride;
@@ -496,8 +498,8 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t tY = tmem_base + lane_off + 128;
     const int row = q_row0 + t * 128 + tid;
     const int nt = n_t[t];
-    const float l2 = row < p.N ? __ldg(p.L + vec_off + row) * kLog2e : CUDART_INF_F;
-    const float dl = row < p.N ? __ldg(p.delta + vec_off + row) : 0.f;
+    const float l2 = row < p.Nq ? __ldg(p.L + vec_off + row) * kLog2e : CUDART_INF_F;
+    const float dl = row < p.Nq ? __ldg(p.delta + vec_off + row) : 0.f;
     const uint64_t scale_log2_2 = pack_f32x2(p.scale_log2, p.scale_log2), scale_2 = pack_f32x2(p.scale, p.scale);
     const uint64_t neg_l2_2 = pack_f32x2(-l2, -l2), neg_dls_2 = pack_f32x2(-dl * p.scale, -dl * p.scale);
     for (int s = 0; s < nt; ++s) {
@@ -564,12 +566,18 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         uint32_t a[32];
         tmem_ld32(tAcc + c * 32, a);
         tmem_wait_ld();
-        if (row < p.N) {
+        if (row < p.Nq) {
           float4 *d4 = reinterpret_cast<float4 *>(dst + c * 32);
 #pragma unroll
-          for (int e = 0; e < 8; ++e)
-            d4[e] = make_float4(__uint_as_float(a[4 * e]), __uint_as_float(a[4 * e + 1]),
-                                __uint_as_float(a[4 * e + 2]), __uint_as_float(a[4 * e + 3]));
+          for (int e = 0; e < 8; ++e) {
+            float4 v = make_float4(__uint_as_float(a[4 * e]), __uint_as_float(a[4 * e + 1]),
+                                   __uint_as_float(a[4 * e + 2]), __uint_as_float(a[4 * e + 3]));
+            if (p.acc_dq) {  // single owner per element: a plain read-add-write is deterministic
+              const float4 o = d4[e];
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            d4[e] = v;
+          }
         }
       }
     }
@@ -664,8 +672,7 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 }
 
 template <int D, int IS_BF16>
-int launch_bwd_impl(const void *O, const void *dO, float *delta, const CUtensorMap *maps, const BwdParams &p, int B,
-                    cudaStream_t stream) {
+int launch_bwd_impl(const CUtensorMap *maps, const BwdParams &p, int B, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     FA_CUDA_CHECK(cudaFuncSetAttribute(bwd_dkdv_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -675,21 +682,87 @@ int launch_bwd_impl(const void *O, const void *dO, float *delta, const CUtensorM
     configured = true;
   }
   // maps: [0] Q, [1] K, [2] V, [3] dO, all with 128-row boxes
-  bwd_delta_kernel<D, IS_BF16><<<dim3((p.N + 7) / 8, p.H, B), 256, 0, stream>>>(
-      reinterpret_cast<const uint16_t *>(O), reinterpret_cast<const uint16_t *>(dO), delta, p.N, p.H,
-      p.batch_stride, p.head_stride);
-  FA_CUDA_CHECK(cudaGetLastError());
-  bwd_dkdv_kernel<D, IS_BF16><<<dim3((p.N + 127) / 128, p.H, B), kBwdThreads, DkdvCfg<D>::kSmemBytes, stream>>>(
-      maps[0], maps[1], maps[2], maps[3], p);
-  FA_CUDA_CHECK(cudaGetLastError());
-  bwd_dq_kernel<D, IS_BF16><<<dim3((p.N + 255) / 256, p.H, B), kBwdThreads, DqCfg<D>::kSmemBytes, stream>>>(
-      maps[0], maps[1], maps[2], maps[3], p);
-  FA_CUDA_CHECK(cudaGetLastError());
-  count_launch(3);
+  if (p.dK != nullptr) {
+    bwd_dkdv_kernel<D, IS_BF16><<<dim3((p.Nk + 127) / 128, p.H, B), kBwdThreads, DkdvCfg<D>::kSmemBytes, stream>>>(
+        maps[0], maps[1], maps[2], maps[3], p);
+    FA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
+  if (p.dQ != nullptr) {
+    bwd_dq_kernel<D, IS_BF16><<<dim3((p.Nq + 255) / 256, p.H, B), kBwdThreads, DqCfg<D>::kSmemBytes, stream>>>(
+        maps[0], maps[1], maps[2], maps[3], p);
+    FA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+  }
   return FA_OK;
 }
 
 }  // namespace
+
+// D_i = rowsum(O o dO) into `delta` ([B, H, Nq] addressed like L: offset / D + row)
+int launch_bwd_delta(const void *O, const void *dO, float *delta, int Nq, int D, int64_t batch_stride,
+                     int64_t head_stride, int B, int H, int dtype, cudaStream_t stream) {
+  const dim3 grid((Nq + 7) / 8, H, B);
+  const uint16_t *o = reinterpret_cast<const uint16_t *>(O), *g = reinterpret_cast<const uint16_t *>(dO);
+  if (D == 64) {
+    if (dtype == FA_DTYPE_BF16) bwd_delta_kernel<64, 1><<<grid, 256, 0, stream>>>(o, g, delta, Nq, H, batch_stride, head_stride);
+    else bwd_delta_kernel<64, 0><<<grid, 256, 0, stream>>>(o, g, delta, Nq, H, batch_stride, head_stride);
+  } else {
+    if (dtype == FA_DTYPE_BF16) bwd_delta_kernel<128, 1><<<grid, 256, 0, stream>>>(o, g, delta, Nq, H, batch_stride, head_stride);
+    else bwd_delta_kernel<128, 0><<<grid, 256, 0, stream>>>(o, g, delta, Nq, H, batch_stride, head_stride);
+  }
+  FA_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return FA_OK;
+}
+
+// Rectangular backward block: gradients of attention(Q[Nq], K[Nk], V[Nk]) given L and delta of the
+// FULL softmax rows.  dK/dV (both or neither) are overwritten; dQ is overwritten or accumulated.
+int launch_bwd_tc_rect(const void *Q, const void *K, const void *V, const void *dO, const float *L,
+                       const float *delta, float *dQ, float *dK, float *dV, int Nq, int Nk, int D, float scale,
+                       int64_t q_batch_stride, int64_t q_head_stride, int64_t kv_batch_stride,
+                       int64_t kv_head_stride, int is_causal, int acc_dq, int B, int H, int dtype,
+                       cudaStream_t stream) {
+  FA_REQUIRE(Q && K && V && dO && L && delta, "null tensor pointer");
+  FA_REQUIRE((dK == nullptr) == (dV == nullptr), "dK and dV go together");
+  FA_REQUIRE(Nq >= 1 && Nk >= 1, "N must be >= 1 (got %d x %d)", Nq, Nk);
+  FA_REQUIRE(!is_causal || Nq == Nk, "causal attention needs Nq == Nk");
+  FA_REQUIRE(D == 64 || D == 128, "D must be 64 or 128 (got %d)", D);
+  FA_REQUIRE(B >= 1 && H >= 1 && H <= 65535 && B <= 65535, "bad B/H (%d, %d)", B, H);
+  FA_REQUIRE(dtype == FA_DTYPE_FP16 || dtype == FA_DTYPE_BF16, "dtype must be FA_DTYPE_FP16 or FA_DTYPE_BF16");
+  FA_REQUIRE(scale > 0.f, "scale must be positive");
+  FA_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(dO) && aligned16(dQ) && aligned16(dK) &&
+                 aligned16(dV),
+             "tensors must be 16-byte aligned");
+  FA_REQUIRE(q_batch_stride % D == 0 && q_head_stride % D == 0 && kv_batch_stride % 8 == 0 && kv_head_stride % 8 == 0,
+             "Q-side strides must be multiples of D, K/V-side strides multiples of 8");
+  FA_REQUIRE((H == 1 || (q_head_stride >= (int64_t)Nq * D && kv_head_stride >= (int64_t)Nk * D)) &&
+                 (B == 1 || (q_batch_stride >= (int64_t)Nq * D && kv_batch_stride >= (int64_t)Nk * D)),
+             "heads overlap: stride smaller than N*D");
+  CUtensorMap maps[4];
+  int rc;
+  if ((rc = make_tensor_map_bhnd(&maps[0], Q, dtype, Nq, D, H, B, q_head_stride, q_batch_stride, 128)) != FA_OK) return rc;
+  if ((rc = make_tensor_map_bhnd(&maps[1], K, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, 128)) != FA_OK) return rc;
+  if ((rc = make_tensor_map_bhnd(&maps[2], V, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, 128)) != FA_OK) return rc;
+  if ((rc = make_tensor_map_bhnd(&maps[3], dO, dtype, Nq, D, H, B, q_head_stride, q_batch_stride, 128)) != FA_OK) return rc;
+  BwdParams p;
+  p.L = L;
+  p.delta = delta;
+  p.dQ = dQ; p.dK = dK; p.dV = dV;
+  p.Nq = Nq; p.Nk = Nk; p.H = H;
+  p.scale = scale;
+  p.scale_log2 = scale * kLog2e;
+  p.batch_stride = q_batch_stride;
+  p.head_stride = q_head_stride;
+  p.kv_batch_stride = kv_batch_stride;
+  p.kv_head_stride = kv_head_stride;
+  p.causal = is_causal ? 1 : 0;
+  p.acc_dq = acc_dq ? 1 : 0;
+  p.prof = g_fwd_prof;
+  if (D == 64)
+    return dtype == FA_DTYPE_BF16 ? launch_bwd_impl<64, 1>(maps, p, B, stream) : launch_bwd_impl<64, 0>(maps, p, B, stream);
+  return dtype == FA_DTYPE_BF16 ? launch_bwd_impl<128, 1>(maps, p, B, stream) : launch_bwd_impl<128, 0>(maps, p, B, stream);
+}
 
 int launch_bwd_tc(const void *Q, const void *K, const void *V, const void *O, const void *dO,
                   const float *L, float *dQ, float *dK, float *dV, int N, int D, float scale,
@@ -699,14 +772,8 @@ int launch_bwd_tc(const void *Q, const void *K, const void *V, const void *O, co
   FA_REQUIRE(N >= 1, "N must be >= 1 (got %d)", N);
   FA_REQUIRE(D == 64 || D == 128, "D must be 64 or 128 (got %d)", D);
   FA_REQUIRE(B >= 1 && H >= 1 && H <= 65535 && B <= 65535, "bad B/H (%d, %d)", B, H);
-  FA_REQUIRE(dtype == FA_DTYPE_FP16 || dtype == FA_DTYPE_BF16, "dtype must be FA_DTYPE_FP16 or FA_DTYPE_BF16");
-  FA_REQUIRE(scale > 0.f, "scale must be positive");
-  FA_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O) && aligned16(dO) && aligned16(dQ) &&
-                 aligned16(dK) && aligned16(dV),
-             "tensors must be 16-byte aligned");
+  FA_REQUIRE(aligned16(O), "tensors must be 16-byte aligned");
   FA_REQUIRE(batch_stride % D == 0 && head_stride % D == 0, "strides must be multiples of D");
-  FA_REQUIRE((H == 1 || head_stride >= (int64_t)N * D) && (B == 1 || batch_stride >= (int64_t)N * D),
-             "heads overlap: stride smaller than N*D");
   // delta is indexed like L: offset / D + row; its extent follows the strides
   const size_t need = fa_workspace_bytes_backward(N, D, B, H);
   const int64_t last = ((int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * head_stride) / D + N;
@@ -715,28 +782,11 @@ int launch_bwd_tc(const void *Q, const void *K, const void *V, const void *O, co
                      "backward workspace too small: need %zu bytes (fa_workspace_bytes_backward; contiguous "
                      "[B,H,N,D] layout assumed), got %zu",
                      need, workspace_bytes);
-  CUtensorMap maps[4];
-  const void *ptrs[4] = {Q, K, V, dO};
-  int rc;
-  for (int i = 0; i < 4; ++i)
-    if ((rc = make_tensor_map_bhnd(&maps[i], ptrs[i], dtype, N, D, H, B, head_stride, batch_stride, 128)) != FA_OK) return rc;
-  BwdParams p;
-  p.L = L;
-  p.delta = reinterpret_cast<const float *>(workspace);
-  p.dQ = dQ; p.dK = dK; p.dV = dV;
-  p.N = N; p.H = H;
-  p.scale = scale;
-  p.scale_log2 = scale * kLog2e;
-  p.batch_stride = batch_stride;
-  p.head_stride = head_stride;
-  p.causal = is_causal ? 1 : 0;
-  p.prof = g_fwd_prof;
   float *delta = reinterpret_cast<float *>(workspace);
-  if (D == 64)
-    return dtype == FA_DTYPE_BF16 ? launch_bwd_impl<64, 1>(O, dO, delta, maps, p, B, stream)
-                                  : launch_bwd_impl<64, 0>(O, dO, delta, maps, p, B, stream);
-  return dtype == FA_DTYPE_BF16 ? launch_bwd_impl<128, 1>(O, dO, delta, maps, p, B, stream)
-                                : launch_bwd_impl<128, 0>(O, dO, delta, maps, p, B, stream);
+  int rc = launch_bwd_delta(O, dO, delta, N, D, batch_stride, head_stride, B, H, dtype, stream);
+  if (rc != FA_OK) return rc;
+  return launch_bwd_tc_rect(Q, K, V, dO, L, delta, dQ, dK, dV, N, N, D, scale, batch_stride, head_stride, batch_stride,
+                            head_stride, is_causal, 0, B, H, dtype, stream);
 }
 
 }  // namespace fa

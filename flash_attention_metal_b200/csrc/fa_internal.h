@@ -50,4 +50,12 @@ int launch_bwd_tc(const void *Q, const void *K, const void *V, const void *O, co
                   int64_t batch_stride, int64_t head_stride, int is_causal, int B, int H, int dtype,
                   void *workspace, size_t workspace_bytes, cudaStream_t stream);
 
+int launch_bwd_delta(const void *O, const void *dO, float *delta, int Nq, int D, int64_t batch_stride,
+                     int64_t head_stride, int B, int H, int dtype, cudaStream_t stream);
+int launch_bwd_tc_rect(const void *Q, const void *K, const void *V, const void *dO, const float *L,
+                       const float *delta, float *dQ, float *dK, float *dV, int Nq, int Nk, int D, float scale,
+                       int64_t q_batch_stride, int64_t q_head_stride, int64_t kv_batch_stride,
+                       int64_t kv_head_stride, int is_causal, int acc_dq, int B, int H, int dtype,
+                       cudaStream_t stream);
+
 }  // namespace fa
