@@ -28,6 +28,7 @@ EXPORTS = (
     "fa_host_attention_fwd_bwd_half", "fa_host_release",
     "flash_attention_v4_half_rect", "fa_ring_unique_id_bytes", "fa_ring_get_unique_id", "fa_ring_create",
     "fa_ring_destroy", "fa_ring_workspace_bytes", "fa_ring_attention_forward", "fa_ring_plan", "fa_ring_local_rows",
+    "fa_ring_workspace_bytes_backward", "fa_ring_attention_backward",
     "fa_last_error", "fa_version", "fa_device_count", "fa_launch_count", "fa_reset_launch_count",
 )
 
@@ -77,6 +78,9 @@ def lib() -> C.CDLL:
         L.fa_ring_workspace_bytes.argtypes = [i32, i32, i32, i32]
         L.fa_ring_workspace_bytes.restype = sz
         L.fa_ring_attention_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, i32, vp, sz, vp]
+        L.fa_ring_workspace_bytes_backward.argtypes = [i32, i32, i32, i32]
+        L.fa_ring_workspace_bytes_backward.restype = sz
+        L.fa_ring_attention_backward.argtypes = [vp] * 11 + [i32, i32, i32, f32, i32, i32, vp, sz, vp]
         ip = C.POINTER(i32)
         L.fa_ring_plan.argtypes = [i32, i32, i32, i32, i32, ip, ip, ip, ip, ip, ip]
         L.fa_ring_local_rows.argtypes = [i32, i32, i32, i32, C.POINTER(i64), ip]
@@ -172,6 +176,15 @@ class Ring:
         _check(lib().fa_ring_attention_forward(self.handle, _ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(L_out), n_local, D,
                                                H, scale, int(is_causal), dtype, _ptr(workspace), workspace_bytes,
                                                _stream(stream)))
+
+    def workspace_bytes_backward(self, n_local, D, H, dtype) -> int:
+        return int(lib().fa_ring_workspace_bytes_backward(n_local, D, H, dtype))
+
+    def backward(self, Q, K, V, O, dO, L, dQ, dK, dV, n_local, D, H, scale, is_causal, dtype, workspace, workspace_bytes,
+                 stream=None):
+        _check(lib().fa_ring_attention_backward(self.handle, _ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(dO), _ptr(L), _ptr(dQ),
+                                                _ptr(dK), _ptr(dV), n_local, D, H, scale, int(is_causal), dtype,
+                                                _ptr(workspace), workspace_bytes, _stream(stream)))
 
     def close(self):
         if self.handle:

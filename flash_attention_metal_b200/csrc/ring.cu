@@ -84,7 +84,25 @@ struct Ring {
   int rank = 0, world = 1, device = 0;
   cudaStream_t comm_stream = nullptr;
   cudaEvent_t inputs_ready = nullptr, recv_done[2] = {nullptr, nullptr}, compute_done[2] = {nullptr, nullptr};
+  cudaEvent_t add_done[2] = {nullptr, nullptr}, acc_recv_done[2] = {nullptr, nullptr};  // backward dK/dV ring
 };
+
+// Backward dK/dV ring step: out = (has_in ? in : 0) (+ tmp on the key rows this step touched).
+// One launch covers dK and dV ([2][H, n_local, D] fp32 each, stacked).  Single owner per element.
+__global__ void __launch_bounds__(256) ring_dkv_add_kernel(float *__restrict__ out, const float *__restrict__ in,
+                                                           const float *__restrict__ tmp, int64_t per_tensor,
+                                                           int n_local, int D, int k_off, int k_rows, int has_in) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // float4 index within one tensor
+  if (v * 4 >= per_tensor) return;
+  const int64_t e = v * 4 + (int64_t)blockIdx.y * per_tensor;        // blockIdx.y: 0 = dK, 1 = dV
+  const int row = (int)(((v * 4) / D) % n_local);
+  float4 a = has_in ? *reinterpret_cast<const float4 *>(in + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row >= k_off && row < k_off + k_rows) {
+    const float4 t = *reinterpret_cast<const float4 *>(tmp + e);
+    a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+  }
+  *reinterpret_cast<float4 *>(out + e) = a;
+}
 
 // ---- merge kernel: acc <- acc (+) part, optionally writing the final 16-bit O and L ----
 // One thread per 8 output elements of a row; O_acc fp32 [H, n_local, D], part 16-bit.
@@ -207,6 +225,8 @@ int fa_ring_create(void **ring_out, const void *unique_id, int rank, int world, 
   for (int i = 0; i < 2; ++i) {
     FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->recv_done[i], cudaEventDisableTiming));
     FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->compute_done[i], cudaEventDisableTiming));
+    FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->add_done[i], cudaEventDisableTiming));
+    FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->acc_recv_done[i], cudaEventDisableTiming));
   }
   *ring_out = r;
   return FA_OK;
@@ -223,6 +243,8 @@ int fa_ring_destroy(void *ring) {
   for (int i = 0; i < 2; ++i) {
     if (r->recv_done[i]) cudaEventDestroy(r->recv_done[i]);
     if (r->compute_done[i]) cudaEventDestroy(r->compute_done[i]);
+    if (r->add_done[i]) cudaEventDestroy(r->add_done[i]);
+    if (r->acc_recv_done[i]) cudaEventDestroy(r->acc_recv_done[i]);
   }
   delete r;
   return FA_OK;
@@ -352,6 +374,121 @@ int fa_ring_attention_forward(void *ring, const void *Q, const void *K, const vo
       curV = slot[s & 1] + tile_bytes;
     }
   }
+  return FA_OK;
+}
+
+size_t fa_ring_workspace_bytes_backward(int n_local, int D, int H, int dtype) {
+  (void)dtype;
+  if (n_local < 1 || H < 1 || D < 1) return 0;
+  const size_t tile = (size_t)H * n_local * D;
+  size_t bytes = 2 * (2 * tile * 2)        // two K|V receive slots (16-bit)
+                 + 2 * tile * 4            // this step's dK|dV block (fp32)
+                 + 2 * (2 * tile * 4)      // two outgoing dK|dV accumulators
+                 + 2 * tile * 4            // incoming dK|dV accumulator
+                 + (size_t)H * n_local * 4;  // delta
+  return bytes + 1024;
+}
+
+// Ring backward: K/V chunks travel one step ahead of the tile loop (as in the forward); the dK/dV
+// accumulator of a chunk travels one step behind it -- each rank adds the contribution of its own
+// queries and passes the sum on, and after the last step one more hop returns the finished dK/dV to
+// the owner.  dQ accumulates in place on the owning rank.  Every sum has a fixed order: results are
+// run-to-run deterministic.  L must be the final log-sum-exp written by fa_ring_attention_forward.
+int fa_ring_attention_backward(void *ring, const void *Q, const void *K, const void *V, const void *O,
+                               const void *dO, const float *L, float *dQ, float *dK, float *dV, int n_local, int D,
+                               int H, float scale, int is_causal, int dtype, void *workspace, size_t workspace_bytes,
+                               fa_stream_t stream_) {
+  Ring *r = reinterpret_cast<Ring *>(ring);
+  FA_REQUIRE(r && Q && K && V && O && dO && L && dQ && dK && dV, "null argument");
+  FA_REQUIRE(D == 64 || D == 128, "D must be 64 or 128 (got %d)", D);
+  FA_REQUIRE(!is_causal || n_local % 2 == 0, "causal ring attention needs an even n_local");
+  FA_REQUIRE(n_local % 8 == 0, "n_local must be a multiple of 8");
+  const size_t need = fa_ring_workspace_bytes_backward(n_local, D, H, dtype);
+  if (!workspace || workspace_bytes < need)
+    return set_error(FA_ERR_WORKSPACE, "ring backward workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  NcclApi *api = nccl();
+  if (!api) return set_error(FA_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  cudaStream_t st = (cudaStream_t)stream_;
+  const int P = r->world;
+  const size_t tile_elems = (size_t)H * n_local * D;
+  const size_t kv_bytes = tile_elems * 2, g_bytes = tile_elems * 4;
+  char *ws = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  char *slot[2] = {ws, ws + 2 * kv_bytes};
+  float *tmp = reinterpret_cast<float *>(ws + 4 * kv_bytes);                  // [dK | dV] of this step's block
+  float *acc_out[2] = {tmp + 2 * tile_elems, tmp + 4 * tile_elems};
+  float *acc_in = tmp + 6 * tile_elems;
+  float *delta = tmp + 8 * tile_elems;
+  const int next = (r->rank + 1) % P, prev = (r->rank - 1 + P) % P;
+  const int64_t hs = (int64_t)n_local * D;
+  int rc = launch_bwd_delta(O, dO, delta, n_local, D, (int64_t)H * hs, hs, 1, H, dtype, st);
+  if (rc != FA_OK) return rc;
+  FA_CUDA_CHECK(cudaEventRecord(r->inputs_ready, st));
+  const void *curK = K, *curV = V;
+  if (P > 1) {  // A(0): our own chunk starts travelling
+    FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->inputs_ready, 0));
+    FA_NCCL_CHECK(api->GroupStart());
+    FA_NCCL_CHECK(api->Send(curK, kv_bytes, kNcclUint8, next, r->comm, r->comm_stream));
+    FA_NCCL_CHECK(api->Send(curV, kv_bytes, kNcclUint8, next, r->comm, r->comm_stream));
+    FA_NCCL_CHECK(api->Recv(slot[0], kv_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+    FA_NCCL_CHECK(api->Recv(slot[0] + kv_bytes, kv_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+    FA_NCCL_CHECK(api->GroupEnd());
+    FA_CUDA_CHECK(cudaEventRecord(r->recv_done[0], r->comm_stream));
+  }
+  for (int s = 0; s < P; ++s) {
+    Block b;
+    ring_plan(r->rank, P, s, n_local, is_causal, &b);
+    const uint16_t *q = reinterpret_cast<const uint16_t *>(Q) + (int64_t)b.q_off * D;
+    const uint16_t *g = reinterpret_cast<const uint16_t *>(dO) + (int64_t)b.q_off * D;
+    const uint16_t *k = reinterpret_cast<const uint16_t *>(curK) + (int64_t)b.k_off * D;
+    const uint16_t *v = reinterpret_cast<const uint16_t *>(curV) + (int64_t)b.k_off * D;
+    float *blk_dk = (P == 1 ? dK : tmp) + (int64_t)b.k_off * D;
+    float *blk_dv = (P == 1 ? dV : tmp + tile_elems) + (int64_t)b.k_off * D;
+    rc = launch_bwd_tc_rect(q, k, v, g, L + b.q_off, delta + b.q_off, dQ + (int64_t)b.q_off * D, blk_dk, blk_dv, b.q_rows,
+                            b.k_rows, D, scale, (int64_t)H * hs, hs, (int64_t)H * hs, hs, b.causal, s > 0, 1, H, dtype, st);
+    if (rc != FA_OK) return rc;
+    if (P == 1) break;
+    // ---- dK/dV accumulator of the chunk we hold: add our block, pass it on ----
+    if (s > 0) FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->acc_recv_done[s & 1], 0));
+    {
+      const int64_t vecs = (int64_t)tile_elems / 4;
+      dim3 grid((unsigned)((vecs + 255) / 256), 2);
+      ring_dkv_add_kernel<<<grid, 256, 0, st>>>(acc_out[s & 1], acc_in, tmp, (int64_t)tile_elems, n_local, D, b.k_off,
+                                                b.k_rows, s > 0);
+      FA_CUDA_CHECK(cudaGetLastError());
+      count_launch();
+    }
+    FA_CUDA_CHECK(cudaEventRecord(r->add_done[s & 1], st));
+    FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->add_done[s & 1], 0));
+    FA_NCCL_CHECK(api->GroupStart());
+    FA_NCCL_CHECK(api->Send(acc_out[s & 1], g_bytes, kNcclUint8, next, r->comm, r->comm_stream));
+    FA_NCCL_CHECK(api->Send(acc_out[s & 1] + tile_elems, g_bytes, kNcclUint8, next, r->comm, r->comm_stream));
+    if (s + 1 < P) {
+      FA_NCCL_CHECK(api->Recv(acc_in, g_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+      FA_NCCL_CHECK(api->Recv(acc_in + tile_elems, g_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+    } else {  // last hop: the finished gradients of our own chunk come home
+      FA_NCCL_CHECK(api->Recv(dK, g_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+      FA_NCCL_CHECK(api->Recv(dV, g_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+    }
+    FA_NCCL_CHECK(api->GroupEnd());
+    FA_CUDA_CHECK(cudaEventRecord(r->acc_recv_done[(s + 1) & 1], r->comm_stream));
+    // ---- K/V: switch to the chunk that arrived, forward it if somebody still needs it ----
+    if (s + 1 < P) {
+      FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->recv_done[s & 1], 0));
+      curK = slot[s & 1];
+      curV = slot[s & 1] + kv_bytes;
+      if (s + 2 < P) {  // the other slot was read by step s, which the comm stream has already waited for
+        char *dst = slot[(s + 1) & 1];
+        FA_NCCL_CHECK(api->GroupStart());
+        FA_NCCL_CHECK(api->Send(curK, kv_bytes, kNcclUint8, next, r->comm, r->comm_stream));
+        FA_NCCL_CHECK(api->Send(curV, kv_bytes, kNcclUint8, next, r->comm, r->comm_stream));
+        FA_NCCL_CHECK(api->Recv(dst, kv_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+        FA_NCCL_CHECK(api->Recv(dst + kv_bytes, kv_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+        FA_NCCL_CHECK(api->GroupEnd());
+        FA_CUDA_CHECK(cudaEventRecord(r->recv_done[(s + 1) & 1], r->comm_stream));
+      }
+    }
+  }
+  if (P > 1) FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->acc_recv_done[P & 1], 0));
   return FA_OK;
 }
 

@@ -135,6 +135,14 @@ size_t fa_ring_workspace_bytes(int n_local, int D, int H, int dtype);
 int fa_ring_attention_forward(fa_ring_t ring, const void *Q, const void *K, const void *V, void *O,
                               float *L_out, int n_local, int D, int H, float scale, int is_causal,
                               int dtype, void *workspace, size_t workspace_bytes, fa_stream_t stream);
+/* Backward of the same layout: L is the log-sum-exp written by fa_ring_attention_forward, O its
+ * output.  dQ, dK, dV are fp32 [H, n_local, D], fully overwritten, deterministic.  K/V chunks
+ * travel one step ahead of the tile loop, each chunk's dK/dV accumulator one step behind it. */
+size_t fa_ring_workspace_bytes_backward(int n_local, int D, int H, int dtype);
+int fa_ring_attention_backward(fa_ring_t ring, const void *Q, const void *K, const void *V, const void *O,
+                               const void *dO, const float *L, float *dQ, float *dK, float *dV,
+                               int n_local, int D, int H, float scale, int is_causal, int dtype,
+                               void *workspace, size_t workspace_bytes, fa_stream_t stream);
 /* host-only helpers (no GPU needed): the block a rank computes at a ring step, in local row
  * coordinates, and the global rows a rank owns */
 int fa_ring_plan(int rank, int world, int step, int n_local, int is_causal, int *src_rank, int *q_off,

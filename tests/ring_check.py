@@ -17,6 +17,7 @@ ap.add_argument("--hdim", type=int, default=128)
 ap.add_argument("--causal", type=int, default=1)
 ap.add_argument("--check", type=int, default=1)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--bwd", type=int, default=0)
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
@@ -49,6 +50,27 @@ if a.check:
     err = (O.float() - Of[:, rows].float()).abs().max().item()
     errl = (L - Lf[:, rows]).abs().max().item()
     t = torch.tensor([err, errl], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); err, errl = t.tolist()
+berr = None
+if a.bwd:
+    gd = torch.Generator(device="cuda").manual_seed(2)
+    if a.check:
+        dOf = torch.rand((H, N, D), device="cuda", generator=gd).mul_(2).sub_(1).to(torch.bfloat16)
+        dO = dOf[:, rows].contiguous()
+    else:
+        dO = torch.rand((H, n_local, D), device="cuda", generator=gd).mul_(2).sub_(1).to(torch.bfloat16)
+    dQ, dK, dV = (torch.full((H, n_local, D), float("nan"), device="cuda") for _ in range(3))
+    bwsb = ring.workspace_bytes_backward(n_local, D, H, fa.BF16); bws = torch.empty(bwsb, dtype=torch.uint8, device="cuda")
+    run_b = lambda: ring.backward(Q, K, V, O, dO, L, dQ, dK, dV, n_local, D, H, scale, a.causal, fa.BF16, bws, bwsb, st)
+    run_b(); torch.cuda.synchronize()
+    if a.check:
+        gQ, gK, gV = (torch.empty((H, N, D), device="cuda") for _ in range(3))
+        w1 = fa.workspace_bytes_backward(N, D, 1, H); w1b = torch.empty(w1, dtype=torch.uint8, device="cuda")
+        fa.flash_attention_backward(Qf, Kf, Vf, Of, dOf, Lf, gQ, gK, gV, N, D, scale, H * N * D, N * D, a.causal, 1, H, fa.BF16, w1b, w1)
+        torch.cuda.synchronize()
+        errs = [(x - y[:, rows]).abs().max().item() / y.abs().max().item() for x, y in ((dQ, gQ), (dK, gK), (dV, gV))]
+        t = torch.tensor(errs, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); berr = t.tolist()
+    run_f = run
+    run = lambda: (run_f(), run_b())
 for _ in range(2): run()
 dist.barrier(); torch.cuda.synchronize()
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -56,10 +78,11 @@ ev0.record(st)
 for _ in range(a.reps): run()
 ev1.record(st); torch.cuda.synchronize()
 ms = torch.tensor([ev0.elapsed_time(ev1) / a.reps], device="cuda"); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-flops = 4.0 * H * N * N * D * (0.5 if a.causal else 1.0)
+flops = 4.0 * H * N * N * D * (0.5 if a.causal else 1.0) * (3.5 if a.bwd else 1.0)
 if rank == 0:
     print(json.dumps({"ring_forward": True, "world": world, "N_total": N, "n_local": n_local, "H": H, "d": D, "causal": a.causal,
                       "ms": ms.item(), "tflops_total": flops / ms.item() / 1e9, "tflops_per_gpu": flops / ms.item() / 1e9 / world,
-                      "max_abs_err_vs_single_gpu": err, "max_abs_L_err": errl}), flush=True)
+                      "max_abs_err_vs_single_gpu": err, "max_abs_L_err": errl, "bwd": a.bwd,
+                      "bwd_rel_err_dq_dk_dv_vs_single_gpu": berr}), flush=True)
 ring.close()
 dist.destroy_process_group()

@@ -122,3 +122,55 @@ def test_ring_schedule_emulated_on_one_gpu(fa, world, causal):
             l_acc[sl] = l_new
         assert np.abs(o_acc - want[rows]).max() <= TOL
         assert np.abs(l_acc - want_l[rows]).max() <= 5e-3
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_ring_backward_world_one_matches_oracle(fa, causal):
+    """fa_ring_attention_backward with a one-rank communicator: delta + rectangular backward kernels."""
+    import torch
+
+    H, n, d = 2, 384, 64
+    scale = float(d ** -0.5)
+    bits, f = zip(*(bf16(oracle.init_random(H * n * d, s).reshape(H, n, d)) for s in (11, 12, 13, 14)))
+    Q, K, V, dO = (dev(b.view(np.int16)) for b in bits)
+    ring = fa.Ring(fa.ring_unique_id(), 0, 1, 0)
+    try:
+        O = torch.zeros((H, n, d), dtype=torch.int16, device="cuda")
+        L = torch.zeros((H, n), device="cuda")
+        wsb = ring.workspace_bytes(n, d, H, fa.BF16)
+        ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+        ring.forward(Q, K, V, O, L, n, d, H, scale, causal, fa.BF16, ws, wsb)
+        grads = [torch.full((H, n, d), float("nan"), device="cuda") for _ in range(3)]
+        bwsb = ring.workspace_bytes_backward(n, d, H, fa.BF16)
+        bws = torch.empty(bwsb, dtype=torch.uint8, device="cuda")
+        ring.backward(Q, K, V, O, dO, L, *grads, n, d, H, scale, causal, fa.BF16, bws, bwsb)
+        torch.cuda.synchronize()
+    finally:
+        ring.close()
+    for h in range(H):
+        want = oracle.backward(f[0][h], f[1][h], f[2][h], f[3][h], scale, causal)
+        for g, w in zip(grads, want):
+            err = np.abs(g[h].cpu().numpy() - w).max()
+            assert err <= 2e-2 and err <= 1e-2 * np.abs(w).max()
+
+
+def test_rectangular_backward_blocks_sum_to_full_gradients(fa):
+    """The ring's building block: gradients of attention over two key chunks, each computed by the
+    rectangular backward from the full-row L and delta, add up to the gradients of the whole."""
+    import torch
+
+    n, d, scale = 512, 64, 0.125
+    ring = fa.Ring(fa.ring_unique_id(), 0, 1, 0)
+    ring.close()  # only here to make sure NCCL loading does not interfere; kernels are called directly
+    bits, f = zip(*(bf16(oracle.init_random(n * d, s).reshape(n, d)) for s in (21, 22, 23, 24)))
+    want = oracle.backward(*f, scale, False)
+    Q, K, V, dO = (dev(b.view(np.int16)) for b in bits)
+    O = torch.zeros((n, d), dtype=torch.int16, device="cuda")
+    L = torch.zeros((n,), device="cuda")
+    fa.flash_attention_v4_half(Q, K, V, O, n, d, scale, n * d, n * d, L, False, 1, 1, fa.BF16)
+    got = [torch.zeros((n, d), device="cuda") for _ in range(3)]
+    wsb = fa.workspace_bytes_backward(n, d, 1, 1)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    fa.flash_attention_backward(Q, K, V, O, dO, L, *got, n, d, scale, n * d, n * d, False, 1, 1, fa.BF16, ws, wsb)
+    for g, w in zip(got, want):
+        assert np.abs(g.cpu().numpy() - w).max() <= 1e-2 * np.abs(w).max()
