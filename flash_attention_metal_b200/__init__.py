@@ -80,7 +80,7 @@ def lib() -> C.CDLL:
         L.fa_ring_attention_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, i32, vp, sz, vp]
         L.fa_ring_workspace_bytes_backward.argtypes = [i32, i32, i32, i32]
         L.fa_ring_workspace_bytes_backward.restype = sz
-        L.fa_ring_attention_backward.argtypes = [vp] * 11 + [i32, i32, i32, f32, i32, i32, vp, sz, vp]
+        L.fa_ring_attention_backward.argtypes = [vp] * 10 + [i32, i32, i32, f32, i32, i32, vp, sz, vp]
         ip = C.POINTER(i32)
         L.fa_ring_plan.argtypes = [i32, i32, i32, i32, i32, ip, ip, ip, ip, ip, ip]
         L.fa_ring_local_rows.argtypes = [i32, i32, i32, i32, C.POINTER(i64), ip]

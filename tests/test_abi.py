@@ -64,3 +64,21 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.replace("no oracle", ""), (dirpath, f)
+
+
+def test_ctypes_signatures_match_the_header(fa):
+    """Every prototype in the header has as many parameters as the ctypes binding declares."""
+    text = open(os.path.join(ROOT, "include", "flash_attn_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    lib = fa.lib()
+    checked = 0
+    for m in re.finditer(r"\b([a-z_0-9]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        name, params = m.group(1), m.group(2).strip()
+        if not hasattr(lib, name):
+            continue
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        argtypes = getattr(lib, name).argtypes
+        if argtypes is not None:
+            assert len(argtypes) == n, (name, len(argtypes), n)
+            checked += 1
+    assert checked >= 15
