@@ -198,3 +198,38 @@ def test_host_buffer_fwd_bwd_entry_point(fa):
     assert np.abs(oracle.from_half_bits(o, dtype) - ow).max() <= 2e-2
     assert np.abs(l - lw).max() <= 5e-3
     fa.host_release()
+
+
+def test_no_writes_outside_the_output_tensors(fa):
+    """compute-sanitizer is closed on this pool, so bounds are checked with guard bands: every output
+    sits inside a larger buffer filled with a sentinel, N is ragged (not a multiple of any tile), and
+    the bands must come back untouched."""
+    import torch
+
+    for n, d, causal in ((333, 64, True), (129, 128, False), (1, 64, False)):
+        H, guard = 2, 4096
+        scale = float(d ** -0.5)
+        mk16 = lambda: torch.randn((H, n, d), device="cuda").to(torch.bfloat16)
+        Q, K, V, dO = mk16(), mk16(), mk16(), mk16()
+
+        def guarded(numel, dtype, fill):
+            buf = torch.full((numel + 2 * guard,), fill, dtype=dtype, device="cuda")
+            return buf, buf[guard:guard + numel]
+
+        ob, O = guarded(H * n * d, torch.int16, 0x5A5A)
+        lb, L = guarded(H * n, torch.float32, 12345.0)
+        fa.flash_attention_v4_half(Q, K, V, O, n, d, scale, H * n * d, n * d, L, causal, 1, H, fa.BF16)
+        gb = [guarded(H * n * d, torch.float32, 12345.0) for _ in range(3)]
+        wsb = fa.workspace_bytes_backward(n, d, 1, H)
+        wb, ws = guarded(wsb, torch.uint8, 0x5A)
+        fa.flash_attention_backward(Q, K, V, O, dO, L, gb[0][1], gb[1][1], gb[2][1], n, d, scale, H * n * d, n * d,
+                                    causal, 1, H, fa.BF16, ws, wsb)
+        fb, Of = guarded(n * d, torch.float32, 12345.0)
+        qf = torch.randn((n, d), device="cuda")
+        for f in (fa.naive_attention, fa.flash_attention, fa.flash_attention_v2):
+            f(qf, qf, qf, Of, n, d, scale, causal)
+        torch.cuda.synchronize()
+        for buf, fill in [(ob, 0x5A5A), (lb, 12345.0), (wb, 0x5A), (fb, 12345.0)] + [(g[0], 12345.0) for g in gb]:
+            assert bool((buf[:guard] == fill).all()) and bool((buf[-guard:] == fill).all()), (n, d)
+        assert torch.isfinite(O.view(torch.bfloat16).float()).all()
+        assert all(torch.isfinite(g[1]).all() for g in gb)
