@@ -15,7 +15,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libflash_attn_b200.so")
+# FA_B200_LIB: development override to A/B two builds of the library (never a fallback)
+LIB_PATH = os.environ.get("FA_B200_LIB") or os.path.join(_HERE, "libflash_attn_b200.so")
 
 FP16, BF16 = 0, 1
 NAIVE, V1, V2 = 0, 1, 2

@@ -673,13 +673,12 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
 template <int D, int IS_BF16>
 int launch_bwd_impl(const CUtensorMap *maps, const BwdParams &p, int B, cudaStream_t stream) {
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;  // the attribute is per device
+  if (configured.first_use()) {
     FA_CUDA_CHECK(cudaFuncSetAttribute(bwd_dkdv_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        DkdvCfg<D>::kSmemBytes));
     FA_CUDA_CHECK(cudaFuncSetAttribute(bwd_dq_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        DqCfg<D>::kSmemBytes));
-    configured = true;
   }
   // maps: [0] Q, [1] K, [2] V, [3] dO, all with 128-row boxes
   if (p.dK != nullptr) {

@@ -24,6 +24,18 @@ void count_launch(int n = 1);
     if (!(cond)) return ::fa::set_error(FA_ERR_INVALID, __VA_ARGS__);                  \
   } while (0)
 
+// "once per CUDA device" flag for per-device function attributes (max dynamic shared memory)
+struct DeviceOnce {
+  bool done[64] = {};
+  bool first_use() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // fp32 variants (fp32_kernels.cu).  variant: 0 naive, 1 tiled v1, 2 vectorised v2.

@@ -358,11 +358,10 @@ int launch_fp32_d(int variant, const float *Q, const float *K, const float *V, f
     flash_attention_v1_kernel<D><<<grid, V1_BR, 0, st>>>(Q, K, V, O, N, scale, causal, bs, hs);
   } else {
     const int smem = (int)sizeof(V2Smem<D>);
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;  // the attribute is per device
+    if (configured.first_use()) {
       FA_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_v2_kernel<D>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      configured = true;
     }
     dim3 grid((N + V2_BM - 1) / V2_BM, H, B);
     flash_attention_v2_kernel<D><<<grid, V2_THREADS, smem, st>>>(Q, K, V, O, N, scale, causal, bs, hs);

@@ -363,11 +363,10 @@ template <int D, int IS_BF16>
 int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUtensorMap &tmV,
                        const FwdParams &p, int B, cudaStream_t stream) {
   using Cfg = FwdCfg<D>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;  // the attribute is per device
+  if (configured.first_use()) {
     FA_CUDA_CHECK(cudaFuncSetAttribute(fwd_tc_kernel<D, IS_BF16>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
   }
   dim3 grid((p.Nq + 2 * kBM - 1) / (2 * kBM), p.H, B);
   fwd_tc_kernel<D, IS_BF16><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
