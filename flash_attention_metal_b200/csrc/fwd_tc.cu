@@ -56,7 +56,21 @@ struct FwdCfg {
   static constexpr int kSmemBytes = kSmemTiles + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
+// FA_FWD_TRACE (development builds only): one CTA records clock64() timestamps of its hand-offs
+// for four consecutive iterations into the buffer set with fa_debug_set_prof_buffer.
+#ifdef FA_FWD_TRACE
+#define FA_TRACE(cond, j, slot)                                                                   \
+  do {                                                                                            \
+    if (p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (cond) &&   \
+        (j) >= 8 && (j) < 12)                                                                     \
+      p.prof[((j) - 8) * 64 + (slot)] = clock64();                                                \
+  } while (0)
+#else
+#define FA_TRACE(cond, j, slot) do {} while (0)
+#endif
+
 struct FwdParams {
+  long long *prof;
   void *O;
   float *L;
   int Nq;             // query rows (= rows of O and L)
@@ -103,6 +117,16 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     n_t[t] = r0 >= p.Nq ? 0 : (p.causal ? min(n_kv_all, r0 / kBN + 1) : n_kv_all);
   }
   const int nmax = max(n_t[0], n_t[1]);
+#ifdef FA_FWD_TRACE
+  // SM clock under load: cycles and nanoseconds over the life of the last CTA in launch order
+  if (p.prof != nullptr && threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 &&
+      blockIdx.z == gridDim.z - 1) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.prof[256] = clock64();
+    p.prof[257] = (long long)ns;
+  }
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -143,10 +167,12 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+      FA_TRACE((warp & 3) == 0 && lane == 0, j, t * 5 + 0);
       uint32_t s[4][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32(tS + c * 32, s[c]);
       tmem_wait_ld();
+      FA_TRACE((warp & 3) == 0 && lane == 0, j, t * 5 + 1);
 
       // ---- masks: causal diagonal tile (always the last one) / keys past N ----
       const bool diag = p.causal && (j == nt - 1);
@@ -160,49 +186,14 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i > limit) s[c][i] = 0xff800000u;  // -inf
       }
-      // ---- row max ------------------------------------------------------------
-      float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
-#pragma unroll
-      for (int c = 0; c < 4; ++c)
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[c][i]));
-      const float m_tile = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-      // ---- conditional rescale: only move the reference max when it grows by more
-      //      than 2^threshold; below that P <= 2^threshold, safe in fp32 sums and 16-bit P
-      float acc_scale = 1.f;
-      if (j == 0) {
-        m_run = m_tile;
-      } else {
-        const float grow_log2 = (m_tile - m_run) * p.scale_log2;
-        if (grow_log2 > kRescaleThreshold) {
-          acc_scale = ex2(-grow_log2);
-          m_run = m_tile;
-        }
-      }
-      if (j > 0 && __any_sync(0xffffffffu, acc_scale != 1.f)) {
-        // PV_t(j-1) completed before S_t(j) (in-order tensor pipe), PV_t(j) waits for
-        // p_full below: O_t is quiescent here.
-#pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tO + c * 32, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * acc_scale);
-          tmem_st32(tO + c * 32, o);
-        }
-      }
-      // ---- P = exp2(s * scale_log2 - m * scale_log2), row sum, pack ---------------
-      const float neg_m = -m_run * p.scale_log2;
-      // packed fp32x2 FMA / ADD: one issue slot per two elements (FFMA2 / FADD2)
-      const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2), negm2 = pack_f32x2(neg_m, neg_m);
-      uint64_t sum2[2] = {0ull, 0ull};
-      // P is handed to the MMA warp in two halves of 64 keys: the first four k-steps of
-      // O += P V run while the second half of the exponentials is still being computed
-      // (+3.5 % at D = 128; at D = 64 the PV MMA is too short to pay for the second hand-off,
-      // so both halves are published together there).
-#pragma unroll
-      for (int hlf = 0; hlf < 2; ++hlf) {
+      // P = exp2(s * scale_log2 - m * scale_log2) for one half (64 keys) of the row: packed 16-bit
+      // values into the first 32 (second 32) columns of S, partial row sums into sum2
+      uint64_t sum2[2];
+      auto exp_half = [&](int hlf, float m_ref) {
+        const float neg_m = -m_ref * p.scale_log2;
+        // packed fp32x2 FMA / ADD: one issue slot per two elements (FFMA2 / FADD2)
+        const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2), negm2 = pack_f32x2(neg_m, neg_m);
+        if (hlf == 0) sum2[0] = sum2[1] = 0ull;
         uint32_t pk[32];
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc)
@@ -215,13 +206,57 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             pk[cc * 16 + (i >> 1)] = pack2<IS_BF16>(p0, p1);
           }
         tmem_st32(tS + hlf * 32, pk);
-        if (D == 128 || hlf == 1) {
-          tmem_wait_st();
-          tc_fence_before();
-          if (D == 128) mbar_arrive(&p_full[2 * t + hlf]);
-          else { mbar_arrive(&p_full[2 * t]); mbar_arrive(&p_full[2 * t + 1]); }
+      };
+      auto row_max = [&]() {
+        float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[c][i]));
+        return fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      };
+      // ---- conditional rescale: the reference max only moves when the row max grows by more
+      //      than 2^kRescaleThreshold; below that P <= 2^threshold, safe in fp32 sums and 16-bit P
+      const float m_tile = row_max();
+      if (j == 0) m_run = m_tile;
+      FA_TRACE((warp & 3) == 0 && lane == 0, j, t * 5 + 2);
+      float acc_scale = 1.f;
+      const float grow_log2 = (m_tile - m_run) * p.scale_log2;  // 0 at j == 0
+      const bool moved = grow_log2 > kRescaleThreshold;
+      if (__any_sync(0xffffffffu, moved)) {
+        if (moved) {
+          acc_scale = ex2(-grow_log2);
+          m_run = m_tile;
+        }
+        // PV_t(j-1) completed before S_t(j) (in-order tensor pipe), PV_t(j) waits for
+        // p_full below: O_t is quiescent here.
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tO + c * 32, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * acc_scale);
+          tmem_st32(tO + c * 32, o);
         }
       }
+      exp_half(0, m_run);
+      // P is handed to the MMA warp in two halves of 64 keys: the first four k-steps of
+      // O += P V run while the second half of the exponentials is still being computed
+      // (+3.5 % at D = 128; at D = 64 the PV MMA is too short to pay for the second hand-off,
+      // so both halves are published together there).
+      if (D == 128) {
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[2 * t]);
+      }
+      FA_TRACE((warp & 3) == 0 && lane == 0, j, t * 5 + 3);
+      exp_half(1, m_run);
+      tmem_wait_st();
+      tc_fence_before();
+      if (D == 128) mbar_arrive(&p_full[2 * t + 1]);
+      else { mbar_arrive(&p_full[2 * t]); mbar_arrive(&p_full[2 * t + 1]); }
+      FA_TRACE((warp & 3) == 0 && lane == 0, j, t * 5 + 4);
       const uint64_t st2 = add_f32x2(sum2[0], sum2[1]);
       l_run = l_run * acc_scale + (lo_f32(st2) + hi_f32(st2));
     }
@@ -272,6 +307,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           const int stage = item % Cfg::kStages;
           const int round = item / Cfg::kStages;
           mbar_wait(&kv_empty[stage], (round & 1) ^ 1);
+          FA_TRACE(true, (item >> 1), 40 + (item & 1));
           mbar_arrive_expect_tx(&kv_full[stage], Cfg::kTileBytes);
           const CUtensorMap *map = (item & 1) ? &tmV : &tmK;
 #pragma unroll
@@ -324,23 +360,30 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
         tc_commit(&kv_empty[ks0]);
         for (int j = 0; j < nmax; ++j) {
+          FA_TRACE(true, j, 18);
           const uint32_t vs = wait_full(2 * j + 1);
+          FA_TRACE(true, j, 19);
           const bool more = j + 1 < nmax;
           const uint32_t ks = more ? wait_full(2 * j + 2) : 0u;
+          FA_TRACE(true, j, 20);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             if (j < n_t[t]) {
               mbar_wait(&p_full[2 * t], j & 1);
               tc_fence_after();
+              FA_TRACE(true, j, 21 + t * 5);
               issue_pv(t, 0, vs, j > 0);
               mbar_wait(&p_full[2 * t + 1], j & 1);
               tc_fence_after();
+              FA_TRACE(true, j, 22 + t * 5);
               issue_pv(t, 1, vs, j > 0);
+              FA_TRACE(true, j, 23 + t * 5);
               if (j == n_t[t] - 1) tc_commit(&o_full[t]);
             }
             if (j + 1 < n_t[t]) {
               issue_qk(t, ks);
               tc_commit(&s_full[t]);
+              FA_TRACE(true, j, 25 + t * 5);
             }
           }
           tc_commit(&kv_empty[vs]);
@@ -357,6 +400,15 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+#ifdef FA_FWD_TRACE
+  if (p.prof != nullptr && threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 &&
+      blockIdx.z == gridDim.z - 1) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    p.prof[258] = clock64();
+    p.prof[259] = (long long)ns;
+  }
+#endif
 }
 
 template <int D, int IS_BF16>
@@ -402,6 +454,7 @@ int launch_fwd_tc_rect(const void *Q, const void *K, const void *V, void *O, flo
   if ((rc = make_tensor_map_bhnd(&tmK, K, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, kBN)) != FA_OK) return rc;
   if ((rc = make_tensor_map_bhnd(&tmV, V, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, kBN)) != FA_OK) return rc;
   FwdParams p;
+  p.prof = g_fwd_prof;
   p.O = O;
   p.L = L;
   p.Nq = Nq;

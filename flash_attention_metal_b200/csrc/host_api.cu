@@ -96,17 +96,34 @@ int host_half_impl(const void *Q, const void *K, const void *V, const void *dO, 
         (rc = g_pool.get(9, fa_workspace_bytes_backward(N, D, 1, heads) + 256, &dDelta)))
       return rc;
   }
-  // groups of heads: enough CTAs per group to fill the GPU, enough groups to overlap copies
+  // Groups of heads.  Steady state: enough CTAs per group to fill the GPU, enough groups to overlap
+  // copies.  The device->host direction carries the most bytes (fp32 gradients), so the pipeline is
+  // bound by how early the first result copy can start: the first groups are small (1, 1, 2 heads)
+  // to get results onto the bus quickly, later ones grow to the steady size.
   int per_group = (heads + 7) / 8;
   const int min_heads = (int)((148 * 256 + N - 1) / N);  // ~one wave of 256-row CTAs
   if (per_group < min_heads) per_group = min_heads;
   if (per_group > heads) per_group = heads;
-  int groups = (heads + per_group - 1) / per_group;
-  if (groups > HostPool::kMaxGroups) { groups = HostPool::kMaxGroups; per_group = (heads + groups - 1) / groups; groups = (heads + per_group - 1) / per_group; }
+  int group_h0[HostPool::kMaxGroups], group_nh[HostPool::kMaxGroups], groups = 0;
+  {
+    const int ramp[3] = {1, 1, 2};
+    int h0 = 0;
+    while (h0 < heads) {
+      const int left = heads - h0;
+      int nh = (groups < 3 && ramp[groups] < per_group) ? ramp[groups] : per_group;
+      const int groups_left = HostPool::kMaxGroups - groups;  // never run out of events
+      if ((left + nh - 1) / nh > groups_left) nh = (left + groups_left - 1) / groups_left;
+      if (nh > left) nh = left;
+      group_h0[groups] = h0;
+      group_nh[groups] = nh;
+      ++groups;
+      h0 += nh;
+    }
+  }
   auto at = [](const void *p, size_t off) { return (const void *)((const char *)p + off); };
   auto atw = [](void *p, size_t off) { return (void *)((char *)p + off); };
   for (int g = 0; g < groups; ++g) {
-    const int h0 = g * per_group, nh = (h0 + per_group <= heads ? per_group : heads - h0);
+    const int h0 = group_h0[g], nh = group_nh[g];
     const size_t ob = (size_t)h0 * hb, of = (size_t)h0 * hf, ol = (size_t)h0 * hl;
     FA_CUDA_CHECK(cudaMemcpyAsync(atw(dq_, ob), at(Q, ob), nh * hb, cudaMemcpyHostToDevice, g_pool.s_in));
     FA_CUDA_CHECK(cudaMemcpyAsync(atw(dk_, ob), at(K, ob), nh * hb, cudaMemcpyHostToDevice, g_pool.s_in));

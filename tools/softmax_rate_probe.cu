@@ -59,8 +59,37 @@ void run(long long *d, float *sink) {
          cudaGetErrorString(e));
 }
 
+// pure MUFU.EX2 throughput: 128 independent exponentials per pass
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 1) mufu_probe(long long *out, float *sink, int iters) {
+  float v[128];
+#pragma unroll
+  for (int i = 0; i < 128; ++i) v[i] = -0.01f * (threadIdx.x + i);
+  long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 128; ++i) v[i] = ex2(v[i]) - 1.5f;
+  }
+  long long t1 = clock64();
+  float total = 0.f;
+#pragma unroll
+  for (int i = 0; i < 128; ++i) total += v[i];
+  if (threadIdx.x == 0 && blockIdx.x == 0) out[0] = t1 - t0;
+  sink[blockIdx.x * blockDim.x + threadIdx.x] = total;
+}
+template <int NW>
+void run_mufu(long long *d, float *sink) {
+  const int iters = 2000;
+  mufu_probe<NW><<<148, 32 * NW>>>(d, sink, iters);
+  mufu_probe<NW><<<148, 32 * NW>>>(d, sink, iters);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h; cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
+  printf("MUFU.EX2 + FADD only, warps/SM=%d: %.0f cycles per 128 exponentials per thread  [%s]\n", NW, (double)h / iters, cudaGetErrorString(e));
+}
+
 int main() {
   long long *d; float *sink; cudaMalloc(&d, 64); cudaMalloc(&sink, 148 * 256 * 4);
+  run_mufu<4>(d, sink); run_mufu<8>(d, sink); run_mufu<16>(d, sink);
   run<0, 4>(d, sink); run<4, 4>(d, sink); run<3, 4>(d, sink); run<2, 4>(d, sink);
   run<0, 8>(d, sink); run<4, 8>(d, sink); run<3, 8>(d, sink); run<2, 8>(d, sink);
   return 0;
