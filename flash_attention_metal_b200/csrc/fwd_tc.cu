@@ -45,6 +45,28 @@ constexpr int kLoadWarp = 9;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kRescaleThreshold = 8.0f;  // in log2 units: P may grow to 2^8 before O is rescaled
+// Tuning knobs, measured on B200 (tests/perf_probe.py d64, flagship shapes):
+//  * every FA_FWD_EMU-th pair of exponentials is computed on the FMA pipe instead of MUFU.EX2
+//    (16 / clk / SM: 128 exponentials per row need as many MUFU cycles as the tile's MMAs need
+//    tensor cycles at D = 128, twice as many at D = 64).  1 in 4 is the optimum for both head
+//    dims: an emulated pair costs ~22 issue cycles against 8 + 16 MUFU-pipe cycles
+//    (tools/pipe_rate_probe.cu), so a larger share makes the loop issue-bound.
+//  * P is handed to the MMA warp in FA_FWD_PARTS pieces per tile (4 at D = 128: 32 keys = two
+//    k-steps of O += P V each; 2 at D = 64 where the PV MMA is half as long).
+// 0/2 -> 4/4 at D = 128: 1190 -> 1300 TFLOP/s causal, 1355 -> 1470 non-causal (N = 16384, H = 16);
+// 0/1 -> 4/2 at D = 64: 637 -> 751 causal.
+#ifndef FA_FWD_EMU64
+#define FA_FWD_EMU64 4
+#endif
+#ifndef FA_FWD_EMU128
+#define FA_FWD_EMU128 4
+#endif
+#ifndef FA_FWD_PARTS64
+#define FA_FWD_PARTS64 2
+#endif
+#ifndef FA_FWD_PARTS128
+#define FA_FWD_PARTS128 4
+#endif
 
 template <int D>
 struct FwdCfg {
@@ -96,11 +118,11 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemTiles);
   uint64_t *q_full = bars;                       // [2]
   uint64_t *s_full = bars + 2;                   // [2]
-  uint64_t *p_full = bars + 4;                   // [2 tiles][2 halves of the key columns]
-  uint64_t *o_full = bars + 8;                   // [2]
-  uint64_t *kv_full = bars + 10;                 // [kStages]
-  uint64_t *kv_empty = bars + 10 + Cfg::kStages; // [kStages]
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 10 + 2 * Cfg::kStages);
+  uint64_t *p_full = bars + 4;                   // [2 tiles][up to 4 parts of the key columns]
+  uint64_t *o_full = bars + 12;                  // [2]
+  uint64_t *kv_full = bars + 14;                 // [kStages]
+  uint64_t *kv_empty = bars + 14 + Cfg::kStages; // [kStages]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 14 + 2 * Cfg::kStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,8 +154,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[2 * i], kBM);
-      mbar_init(&p_full[2 * i + 1], kBM);
+      for (int q = 0; q < 4; ++q) mbar_init(&p_full[4 * i + q], kBM);
       mbar_init(&o_full[i], 1);
     }
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -186,26 +207,32 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           for (int i = 0; i < 32; ++i)
             if (c * 32 + i > limit) s[c][i] = 0xff800000u;  // -inf
       }
-      // P = exp2(s * scale_log2 - m * scale_log2) for one half (64 keys) of the row: packed 16-bit
-      // values into the first 32 (second 32) columns of S, partial row sums into sum2
-      uint64_t sum2[2];
-      auto exp_half = [&](int hlf, float m_ref) {
+      // P = exp2(s * scale_log2 - m * scale_log2) for 32 keys of the row: packed 16-bit values
+      // into 16 columns of S, partial row sums into sum2
+      uint64_t sum2[2] = {0ull, 0ull};
+      constexpr int kEmu = D == 64 ? FA_FWD_EMU64 : FA_FWD_EMU128;
+      constexpr int kParts = D == 64 ? FA_FWD_PARTS64 : FA_FWD_PARTS128;  // P hand-offs per tile
+      auto exp_chunk = [&](int c, float m_ref) {
         const float neg_m = -m_ref * p.scale_log2;
         // packed fp32x2 FMA / ADD: one issue slot per two elements (FFMA2 / FADD2)
         const uint64_t scale2 = pack_f32x2(p.scale_log2, p.scale_log2), negm2 = pack_f32x2(neg_m, neg_m);
-        if (hlf == 0) sum2[0] = sum2[1] = 0ull;
-        uint32_t pk[32];
+        uint32_t pk[16];
 #pragma unroll
-        for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const int c = hlf * 2 + cc;
-            const uint64_t x2 = fma_f32x2(pack_u32x2(s[c][i], s[c][i + 1]), scale2, negm2);
-            const float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
-            sum2[(i >> 1) & 1] = add_f32x2(sum2[(i >> 1) & 1], pack_f32x2(p0, p1));
-            pk[cc * 16 + (i >> 1)] = pack2<IS_BF16>(p0, p1);
+        for (int i = 0; i < 32; i += 2) {
+          const uint64_t x2 = fma_f32x2(pack_u32x2(s[c][i], s[c][i + 1]), scale2, negm2);
+          float p0, p1;
+          if (kEmu > 0 && ((i >> 1) % (kEmu > 0 ? kEmu : 1)) == (kEmu > 0 ? kEmu : 1) - 1) {
+            const uint64_t e2 = exp2_emulated_x2(x2);  // FMA pipe instead of MUFU
+            p0 = lo_f32(e2);
+            p1 = hi_f32(e2);
+          } else {
+            p0 = ex2(lo_f32(x2));
+            p1 = ex2(hi_f32(x2));
           }
-        tmem_st32(tS + hlf * 32, pk);
+          sum2[(i >> 1) & 1] = add_f32x2(sum2[(i >> 1) & 1], pack_f32x2(p0, p1));
+          pk[i >> 1] = pack2<IS_BF16>(p0, p1);
+        }
+        tmem_st16(tS + c * 16, pk);
       };
       auto row_max = [&]() {
         float mx[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
@@ -240,23 +267,18 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           tmem_st32(tO + c * 32, o);
         }
       }
-      exp_half(0, m_run);
-      // P is handed to the MMA warp in two halves of 64 keys: the first four k-steps of
-      // O += P V run while the second half of the exponentials is still being computed
-      // (+3.5 % at D = 128; at D = 64 the PV MMA is too short to pay for the second hand-off,
-      // so both halves are published together there).
-      if (D == 128) {
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive(&p_full[2 * t]);
+      // P is handed to the MMA warp in kParts pieces: the first k-steps of O += P V run while the
+      // later exponentials are still being computed
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        exp_chunk(c, m_run);
+        if ((c + 1) % (4 / kParts) == 0) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&p_full[4 * t + (c + 1) / (4 / kParts) - 1]);
+          FA_TRACE((warp & 3) == 0 && lane == 0, j, t * 5 + 3 + (c == 3));
+        }
       }
-      FA_TRACE((warp & 3) == 0 && lane == 0, j, t * 5 + 3);
-      exp_half(1, m_run);
-      tmem_wait_st();
-      tc_fence_before();
-      if (D == 128) mbar_arrive(&p_full[2 * t + 1]);
-      else { mbar_arrive(&p_full[2 * t]); mbar_arrive(&p_full[2 * t + 1]); }
-      FA_TRACE((warp & 3) == 0 && lane == 0, j, t * 5 + 4);
       const uint64_t st2 = add_f32x2(sum2[0], sum2[1]);
       l_run = l_run * acc_scale + (lo_f32(st2) + hi_f32(st2));
     }
@@ -340,10 +362,11 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                    make_sdesc_sw128(ka + off, 16, 1024), idesc_qk, kk > 0);
           }
         };
-        auto issue_pv = [&](int t, int hlf, uint32_t vstage, bool accumulate) {
+        constexpr int kParts = D == 64 ? FA_FWD_PARTS64 : FA_FWD_PARTS128;
+        auto issue_pv = [&](int t, int part, uint32_t vstage, bool accumulate) {
           const uint32_t va = sKV_addr + vstage * Cfg::kTileBytes;
 #pragma unroll
-          for (int kk = hlf * 4; kk < hlf * 4 + 4; ++kk)
+          for (int kk = part * (8 / kParts); kk < (part + 1) * (8 / kParts); ++kk)
             mma_ts(tmem_base + 256 + t * D, tmem_base + t * kBN + kk * 8,
                    make_sdesc_sw128(va + kk * 2048, Cfg::kChunkBytes, 1024), idesc_pv,
                    (accumulate || kk > 0) ? 1u : 0u);
@@ -369,14 +392,13 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             if (j < n_t[t]) {
-              mbar_wait(&p_full[2 * t], j & 1);
-              tc_fence_after();
-              FA_TRACE(true, j, 21 + t * 5);
-              issue_pv(t, 0, vs, j > 0);
-              mbar_wait(&p_full[2 * t + 1], j & 1);
-              tc_fence_after();
-              FA_TRACE(true, j, 22 + t * 5);
-              issue_pv(t, 1, vs, j > 0);
+#pragma unroll
+              for (int part = 0; part < kParts; ++part) {
+                mbar_wait(&p_full[4 * t + part], j & 1);
+                tc_fence_after();
+                FA_TRACE(part == 0 || part == kParts - 1, j, 21 + t * 5 + (part > 0));
+                issue_pv(t, part, vs, j > 0);
+              }
               FA_TRACE(true, j, 23 + t * 5);
               if (j == n_t[t] - 1) tc_commit(&o_full[t]);
             }

@@ -7,7 +7,8 @@ mkdir -p gpurun_out
 for rep in 1 2; do
 for lib in ab/*.so; do
   echo "== $lib (rep $rep)" >> gpurun_out/ab_$mode.log
-  if [ "$mode" = bwd ]; then FA_B200_LIB=$PWD/$lib timeout 300 python tests/perf_probe.py bwd >> gpurun_out/ab_$mode.log 2>&1
+  if [ "$mode" = d64 ]; then FA_B200_LIB=$PWD/$lib timeout 300 python tests/perf_probe.py d64 >> gpurun_out/ab_$mode.log 2>&1
+  elif [ "$mode" = bwd ]; then FA_B200_LIB=$PWD/$lib timeout 300 python tests/perf_probe.py bwd >> gpurun_out/ab_$mode.log 2>&1
   else FA_B200_LIB=$PWD/$lib timeout 300 python tests/perf_probe.py >> gpurun_out/ab_$mode.log 2>&1; fi
 done
 done

@@ -22,6 +22,14 @@ def bench(B, H, n, d, causal, dtype=fa.BF16, reps=10):
     flop = 4.0 * B * H * n * n * d * (0.5 if causal else 1.0)
     print(f"B={B} H={H} N={n} d={d} causal={int(causal)}: median {ts[len(ts)//2]:.3f} ms best {ts[0]:.3f} ms -> {flop/ts[len(ts)//2]/1e9:.1f} TFLOP/s (best {flop/ts[0]/1e9:.1f})", flush=True)
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "d64":
+    bench(8, 12, 4096, 64, True)
+    bench(8, 12, 4096, 64, False)
+    bench(1, 16, 16384, 64, True)
+    bench(1, 16, 16384, 64, False)
+    bench(1, 16, 16384, 128, True)
+    bench(1, 16, 16384, 128, False)
+
 if __name__ == "__main__" and len(sys.argv) == 1:
     bench(1, 16, 16384, 128, True)
     bench(1, 16, 16384, 128, False)
