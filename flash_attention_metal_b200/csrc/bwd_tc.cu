@@ -44,7 +44,25 @@ constexpr int kBwdThreads = 384;
 constexpr int kMmaWarp = 8;
 constexpr int kLoadWarp = 9;
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr bool kEmulateHalfExp = false;  // dK/dV phase 1: measured neutral (the GPU is power-capped at this load), kept off
+// Every FA_BWD_EMU-th pair of exponentials runs on the FMA pipe instead of MUFU.EX2 (0 = none), as in
+// the forward kernel; P^T / dS^T / dS are handed to the MMA warp in parts so the accumulating MMAs
+// start while the rest of the tile is still being computed.
+#ifndef FA_BWD_EMU
+#define FA_BWD_EMU 3
+#endif
+#ifndef FA_BWD_SPLIT
+#define FA_BWD_SPLIT 1
+#endif
+constexpr int kBwdEmu = FA_BWD_EMU;
+constexpr int kDkdvParts = FA_BWD_SPLIT ? 2 : 1;  // hand-offs per phase in bwd_dkdv_kernel
+constexpr int kDqParts = FA_BWD_SPLIT ? 4 : 1;    // dS hand-offs per item in bwd_dq_kernel
+__device__ __forceinline__ bool emulate_pair(int pair_index) {
+  return kBwdEmu > 0 && (pair_index % (kBwdEmu > 0 ? kBwdEmu : 1)) == (kBwdEmu > 0 ? kBwdEmu : 1) - 1;
+}
+// 2^x of a packed pair: MUFU.EX2 or the FMA-pipe polynomial
+__device__ __forceinline__ uint64_t exp2_pair(uint64_t x2, bool emulate) {
+  return emulate ? exp2_emulated_x2(x2) : pack_f32x2(ex2(lo_f32(x2)), ex2(hi_f32(x2)));
+}
 
 struct BwdParams {
   const float *L;      // [B, H, N] log-sum-exp of the scaled scores (natural log)
@@ -163,9 +181,9 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t *acc_full = bars + 1;    // dV, dK final
   uint64_t *x_full = bars + 2;      // S^T ready
   uint64_t *y_full = bars + 3;      // dP^T ready
-  uint64_t *p_ready = bars + 4;     // P^T stored by both warpgroups
-  uint64_t *ds_ready = bars + 5;    // dS^T stored by both warpgroups
-  uint64_t *q_full = bars + 6;                       // [kQSlots]
+  uint64_t *p_ready = bars + 4;     // [2] P^T part stored by both warpgroups
+  uint64_t *ds_ready = bars + 6;    // [2] dS^T part stored by both warpgroups
+  uint64_t *q_full = bars + 8;                       // [kQSlots]
   uint64_t *q_empty = q_full + Cfg::kQSlots;
   uint64_t *do_full = q_empty + Cfg::kQSlots;        // [kDoSlots]
   uint64_t *do_empty = do_full + Cfg::kDoSlots;
@@ -185,8 +203,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(acc_full, 1);
     mbar_init(x_full, 1);
     mbar_init(y_full, 1);
-    mbar_init(p_ready, 256);
-    mbar_init(ds_ready, 256);
+    for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 256); mbar_init(&ds_ready[i], 256); }
     for (int i = 0; i < Cfg::kQSlots; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < Cfg::kDoSlots; ++i) { mbar_init(&do_full[i], 1); mbar_init(&do_empty[i], 1); }
     fence_barrier_init();
@@ -234,77 +251,73 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_wait_ld();
       const bool diag = p.causal && (q0 < key0 + 128);
       const uint32_t ld_s = smem_u32(ld);
-      {
-        uint32_t pk[32];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t pk[16];
         if (!diag) {
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int e = 0; e < 32; e += 4) {
-              uint64_t la, lb;  // -L*log2e of four consecutive query columns
-              lds_v2b64(ld_s + (c * 32 + e) * 4, la, lb);
-              const uint64_t xa = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, la);
-              const uint64_t xb = fma_f32x2(pack_u32x2(pr[c][e + 2], pr[c][e + 3]), scale_log2_2, lb);
-              // both warpgroups run this phase at the same time, two warps per scheduler sharing
-              // one MUFU unit: every second pair goes to the FMA pipe instead
-              const float p0 = ex2(lo_f32(xa)), p1 = ex2(hi_f32(xa));
-              const uint64_t pb = kEmulateHalfExp ? exp2_emulated_x2(xb) : pack_f32x2(ex2(lo_f32(xb)), ex2(hi_f32(xb)));
-              const float p2 = lo_f32(pb), p3 = hi_f32(pb);
-              pr[c][e] = __float_as_uint(p0); pr[c][e + 1] = __float_as_uint(p1);
-              pr[c][e + 2] = __float_as_uint(p2); pr[c][e + 3] = __float_as_uint(p3);
-              pk[c * 16 + (e >> 1)] = pack2<IS_BF16>(p0, p1);
-              pk[c * 16 + (e >> 1) + 1] = pack2<IS_BF16>(p2, p3);
-            }
+          for (int e = 0; e < 32; e += 4) {
+            uint64_t la, lb;  // -L*log2e of four consecutive query columns
+            lds_v2b64(ld_s + (c * 32 + e) * 4, la, lb);
+            const uint64_t xa = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, la);
+            const uint64_t xb = fma_f32x2(pack_u32x2(pr[c][e + 2], pr[c][e + 3]), scale_log2_2, lb);
+            // both warpgroups run this phase at the same time, two warps per scheduler sharing
+            // one MUFU unit: a share of the pairs goes to the FMA pipe instead
+            const uint64_t pa = exp2_pair(xa, emulate_pair(e >> 1)), pb = exp2_pair(xb, emulate_pair((e >> 1) + 1));
+            pr[c][e] = __float_as_uint(lo_f32(pa)); pr[c][e + 1] = __float_as_uint(hi_f32(pa));
+            pr[c][e + 2] = __float_as_uint(lo_f32(pb)); pr[c][e + 3] = __float_as_uint(hi_f32(pb));
+            pk[e >> 1] = pack2<IS_BF16>(lo_f32(pa), hi_f32(pa));
+            pk[(e >> 1) + 1] = pack2<IS_BF16>(lo_f32(pb), hi_f32(pb));
+          }
         } else {  // diagonal tile: keys after the query are masked
 #pragma unroll
-          for (int c = 0; c < 2; ++c)
-#pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              uint64_t la, lb;
-              lds_v2b64(ld_s + (c * 32 + (e & ~3)) * 4, la, lb);
-              const uint64_t x2 = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, (e & 2) ? lb : la);
-              float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
-              if (key > q0 + c * 32 + e) p0 = 0.f;
-              if (key > q0 + c * 32 + e + 1) p1 = 0.f;
-              pr[c][e] = __float_as_uint(p0);
-              pr[c][e + 1] = __float_as_uint(p1);
-              pk[c * 16 + (e >> 1)] = pack2<IS_BF16>(p0, p1);
-            }
+          for (int e = 0; e < 32; e += 2) {
+            uint64_t la, lb;
+            lds_v2b64(ld_s + (c * 32 + (e & ~3)) * 4, la, lb);
+            const uint64_t x2 = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, (e & 2) ? lb : la);
+            float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
+            if (key > q0 + c * 32 + e) p0 = 0.f;
+            if (key > q0 + c * 32 + e + 1) p1 = 0.f;
+            pr[c][e] = __float_as_uint(p0);
+            pr[c][e + 1] = __float_as_uint(p1);
+            pk[e >> 1] = pack2<IS_BF16>(p0, p1);
+          }
         }
-        tmem_st32(tX, pk);
+        tmem_st16(tX + c * 16, pk);
+        if (kDkdvParts == 2 || c == 1) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&p_ready[kDkdvParts == 2 ? c : 0]);
+        }
       }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(p_ready);
       // ---- phase 2: dS^T = P^T o (dP^T * scale - D * scale) ----
       long long c2 = prof ? clock64() : 0;
       mbar_wait(y_full, i & 1);
       long long c3 = prof ? clock64() : 0;
       tc_fence_after();
-      {
-        uint32_t dk[32];
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          uint32_t y[32];
-          tmem_ld32(tY + c * 32, y);
-          tmem_wait_ld();
+      for (int c = 0; c < 2; ++c) {
+        uint32_t y[32], dk[16];
+        tmem_ld32(tY + c * 32, y);
+        tmem_wait_ld();
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            uint64_t da, db;  // -D*scale of four consecutive query columns
-            lds_v2b64(ld_s + (64 + c * 32 + e) * 4, da, db);
-            const uint64_t ga = fma_f32x2(pack_u32x2(y[e], y[e + 1]), scale_2, da);
-            const uint64_t gb = fma_f32x2(pack_u32x2(y[e + 2], y[e + 3]), scale_2, db);
-            const uint64_t d2a = mul_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), ga);
-            const uint64_t d2b = mul_f32x2(pack_u32x2(pr[c][e + 2], pr[c][e + 3]), gb);
-            dk[c * 16 + (e >> 1)] = pack2<IS_BF16>(lo_f32(d2a), hi_f32(d2a));
-            dk[c * 16 + (e >> 1) + 1] = pack2<IS_BF16>(lo_f32(d2b), hi_f32(d2b));
-          }
+        for (int e = 0; e < 32; e += 4) {
+          uint64_t da, db;  // -D*scale of four consecutive query columns
+          lds_v2b64(ld_s + (64 + c * 32 + e) * 4, da, db);
+          const uint64_t ga = fma_f32x2(pack_u32x2(y[e], y[e + 1]), scale_2, da);
+          const uint64_t gb = fma_f32x2(pack_u32x2(y[e + 2], y[e + 3]), scale_2, db);
+          const uint64_t d2a = mul_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), ga);
+          const uint64_t d2b = mul_f32x2(pack_u32x2(pr[c][e + 2], pr[c][e + 3]), gb);
+          dk[e >> 1] = pack2<IS_BF16>(lo_f32(d2a), hi_f32(d2a));
+          dk[(e >> 1) + 1] = pack2<IS_BF16>(lo_f32(d2b), hi_f32(d2b));
         }
-        tmem_st32(tY, dk);
+        tmem_st16(tY + c * 16, dk);  // columns [16c, 16c+16) of my half were read in chunk <= c
+        if (kDkdvParts == 2 || c == 1) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&ds_ready[kDkdvParts == 2 ? c : 0]);
+        }
       }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(ds_ready);
       if (prof) { tw_x += c1 - c0; t_p1 += c2 - c1; tw_y += c3 - c2; t_p2 += clock64() - c3; }
     }
     if (prof) {
@@ -383,23 +396,35 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         issue_y(0);
         for (int i = 0; i < n; ++i) {
           long long w0 = mprof ? clock64() : 0;
-          mbar_wait(p_ready, i & 1);
-          if (mprof) mw_p += clock64() - w0;
-          tc_fence_after();
+          // dV += P^T dO_i (K = 128 query rows); part c = columns [32c, 32c+32) of both warpgroups'
+          // halves = k-steps {2c, 2c+1, 4+2c, 5+2c}
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)  // dV += P^T dO_i   (K = 128 query rows)
-            mma_ts(tdV, tX + (kk >> 2) * 64 + (kk & 3) * 8, mnmajor_desc(do_addr(i), kk), idesc_acc,
-                   (i > 0 || kk > 0) ? 1u : 0u);
+          for (int part = 0; part < kDkdvParts; ++part) {
+            mbar_wait(&p_ready[part], i & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int q = 0; q < 8 / kDkdvParts; ++q) {
+              const int kk = kDkdvParts == 2 ? (q >> 1) * 4 + part * 2 + (q & 1) : q;
+              mma_ts(tdV, tX + (kk >> 2) * 64 + (kk & 3) * 8, mnmajor_desc(do_addr(i), kk), idesc_acc,
+                     (i > 0 || part > 0 || q > 0) ? 1u : 0u);
+            }
+          }
+          if (mprof) mw_p += clock64() - w0;
           tc_commit(&do_empty[i % Cfg::kDoSlots]);
           if (i + 1 < n) issue_x(i + 1);
           w0 = mprof ? clock64() : 0;
-          mbar_wait(ds_ready, i & 1);
-          if (mprof) mw_ds += clock64() - w0;
-          tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)  // dK += dS^T Q_i
-            mma_ts(tdK, tY + (kk >> 2) * 64 + (kk & 3) * 8, mnmajor_desc(q_addr(i), kk), idesc_acc,
-                   (i > 0 || kk > 0) ? 1u : 0u);
+          for (int part = 0; part < kDkdvParts; ++part) {  // dK += dS^T Q_i
+            mbar_wait(&ds_ready[part], i & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int q = 0; q < 8 / kDkdvParts; ++q) {
+              const int kk = kDkdvParts == 2 ? (q >> 1) * 4 + part * 2 + (q & 1) : q;
+              mma_ts(tdK, tY + (kk >> 2) * 64 + (kk & 3) * 8, mnmajor_desc(q_addr(i), kk), idesc_acc,
+                     (i > 0 || part > 0 || q > 0) ? 1u : 0u);
+            }
+          }
+          if (mprof) mw_ds += clock64() - w0;
           tc_commit(&q_empty[i % Cfg::kQSlots]);
           if (i == n - 1) tc_commit(acc_full);
           if (i + 1 < n) issue_y(i + 1);
@@ -450,8 +475,8 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint64_t *x_full = bars + 4;      // [2] S of tile t ready
   uint64_t *y_full = bars + 6;      // [2] dP of tile t ready
   uint64_t *x_taken = bars + 8;     // [2] warpgroup t has copied S to registers
-  uint64_t *ds_ready = bars + 10;   // [2] warpgroup t has stored dS
-  uint64_t *k_full = bars + 12;
+  uint64_t *ds_ready = bars + 10;   // [2][4] warpgroup t has stored part c of dS
+  uint64_t *k_full = bars + 18;
   uint64_t *k_empty = k_full + Cfg::kKSlots;
   uint64_t *v_full = k_empty + Cfg::kKSlots;
   uint64_t *v_empty = v_full + Cfg::kVSlots;
@@ -476,7 +501,8 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int i = 0; i < 2; ++i) {
       mbar_init(&res_full[i], 1); mbar_init(&acc_full[i], 1);
       mbar_init(&x_full[i], 1); mbar_init(&y_full[i], 1);
-      mbar_init(&x_taken[i], 128); mbar_init(&ds_ready[i], 128);
+      mbar_init(&x_taken[i], 128);
+      for (int c = 0; c < 4; ++c) mbar_init(&ds_ready[4 * i + c], 128);
     }
     for (int i = 0; i < Cfg::kKSlots; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < Cfg::kVSlots; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
@@ -520,8 +546,9 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             const uint64_t x2 = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, neg_l2_2);
-            pr[c][e] = __float_as_uint(ex2(lo_f32(x2)));
-            pr[c][e + 1] = __float_as_uint(ex2(hi_f32(x2)));
+            const uint64_t p2 = exp2_pair(x2, emulate_pair(e >> 1));
+            pr[c][e] = __float_as_uint(lo_f32(p2));
+            pr[c][e + 1] = __float_as_uint(hi_f32(p2));
           }
       } else {  // diagonal tile: keys after the query are masked
 #pragma unroll
@@ -551,10 +578,12 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           dk[e >> 1] = pack2<IS_BF16>(lo_f32(d2), hi_f32(d2));
         }
         tmem_st16(tY + c * 16, dk);  // columns [16c, 16c+16) were read in chunk <= c
+        if (kDqParts == 4 || c == 3) {
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&ds_ready[4 * t + (kDqParts == 4 ? c : 0)]);
+        }
       }
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&ds_ready[t]);
     }
     if (nt > 0) {
       mbar_wait(&acc_full[t], 0);
@@ -651,12 +680,15 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
             mbar_wait(&x_taken[t], s & 1);  // X is free again
             issue_x(k + 1);
           }
-          mbar_wait(&ds_ready[t], s & 1);
-          tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk)  // dQ_t += dS K_s   (K = 128 keys)
-            mma_ts(tmem_base + 256 + t * D, tY + kk * 8, mnmajor_desc(k_addr(s), kk), idesc_acc,
-                   (s > 0 || kk > 0) ? 1u : 0u);
+          for (int part = 0; part < kDqParts; ++part) {  // dQ_t += dS K_s   (K = 128 keys)
+            mbar_wait(&ds_ready[4 * t + part], s & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int kk = part * (8 / kDqParts); kk < (part + 1) * (8 / kDqParts); ++kk)
+              mma_ts(tmem_base + 256 + t * D, tY + kk * 8, mnmajor_desc(k_addr(s), kk), idesc_acc,
+                     (s > 0 || kk > 0) ? 1u : 0u);
+          }
           if (s == n_t[t] - 1) tc_commit(&acc_full[t]);
           if (k + 1 >= n_items || item_s(k + 1) != s) tc_commit(&k_empty[s % Cfg::kKSlots]);
           if (k + 1 < n_items) issue_y(k + 1);
