@@ -32,6 +32,7 @@
 #include <math_constants.h>
 
 #include "fa_internal.h"
+#include "sched.cuh"
 #include "sm100_ptx.cuh"
 #include "tensormap.h"
 
@@ -74,6 +75,7 @@ struct BwdParams {
   int64_t kv_batch_stride, kv_head_stride;  // elements, of K / V / dK / dV
   int causal;         // requires Nq == Nk
   int acc_dq;         // dQ += instead of dQ = (ring attention accumulates over K/V chunks)
+  int group, n_heads; // dispatch order (sched.cuh)
   long long *prof;  // optional phase-timing buffer (development aid), normally null
 };
 
@@ -190,7 +192,10 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(do_empty + Cfg::kDoSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // dispatch order: see sched.cuh (causal: key tile 0 sees every query tile and goes first)
+  const BlockCoord bc = decode_block(p.group, p.n_heads, p.H);
+  if (bc.b < 0) return;
+  const int j = bc.blk, h = bc.h, b = bc.b;
   const int key0 = j * 128;
   const int n_tiles_all = (p.Nq + 127) / 128;
   const int i_start = p.causal ? j : 0;    // first query tile that sees these keys
@@ -483,8 +488,10 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(v_empty + Cfg::kVSlots);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int qb = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heaviest first
+  const BlockCoord bc = decode_block(p.group, p.n_heads, p.H);
+  if (bc.b < 0) return;
+  const int h = bc.h, b = bc.b;
+  const int qb = p.causal ? ((p.Nq + 255) / 256 - 1 - bc.blk) : bc.blk;  // heaviest first (sched.cuh)
   const int q_row0 = qb * 256;
   const int n_tiles_all = (p.Nk + 127) / 128;
   int n_t[2];
@@ -713,15 +720,19 @@ int launch_bwd_impl(const CUtensorMap *maps, const BwdParams &p, int B, cudaStre
                                        DqCfg<D>::kSmemBytes));
   }
   // maps: [0] Q, [1] K, [2] V, [3] dO, all with 128-row boxes
+  BwdParams q = p;
+  q.n_heads = B * p.H;
+  q.group = dispatch_group(p.causal != 0, (int64_t)2 * (p.Nq > p.Nk ? p.Nq : p.Nk) * D * 2, q.n_heads);
+  if ((p.Nk + 127) / 128 > 65535 || (p.Nq + 255) / 256 > 65535) q.group = 1;  // grid.y limit of the grouped form
   if (p.dK != nullptr) {
-    bwd_dkdv_kernel<D, IS_BF16><<<dim3((p.Nk + 127) / 128, p.H, B), kBwdThreads, DkdvCfg<D>::kSmemBytes, stream>>>(
-        maps[0], maps[1], maps[2], maps[3], p);
+    bwd_dkdv_kernel<D, IS_BF16><<<dispatch_grid(q.group, (p.Nk + 127) / 128, p.H, B), kBwdThreads, DkdvCfg<D>::kSmemBytes, stream>>>(
+        maps[0], maps[1], maps[2], maps[3], q);
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();
   }
   if (p.dQ != nullptr) {
-    bwd_dq_kernel<D, IS_BF16><<<dim3((p.Nq + 255) / 256, p.H, B), kBwdThreads, DqCfg<D>::kSmemBytes, stream>>>(
-        maps[0], maps[1], maps[2], maps[3], p);
+    bwd_dq_kernel<D, IS_BF16><<<dispatch_grid(q.group, (p.Nq + 255) / 256, p.H, B), kBwdThreads, DqCfg<D>::kSmemBytes, stream>>>(
+        maps[0], maps[1], maps[2], maps[3], q);
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();
   }

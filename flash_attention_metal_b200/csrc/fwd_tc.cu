@@ -29,6 +29,7 @@
 #include <math_constants.h>
 
 #include "fa_internal.h"
+#include "sched.cuh"
 #include "sm100_ptx.cuh"
 #include "tensormap.h"
 
@@ -102,6 +103,7 @@ struct FwdParams {
   float scale_log2;   // scale * log2(e)
   int64_t batch_stride, head_stride;  // elements, of Q / O
   int causal;         // requires Nq == Nk
+  int group, n_blocks, n_heads;  // dispatch order (sched.cuh)
 };
 
 template <int D, int IS_BF16>
@@ -126,9 +128,12 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int h = blockIdx.y, b = blockIdx.z;
+  // dispatch order: see sched.cuh (causal: heaviest = latest row blocks first, over groups of heads)
+  const BlockCoord bc = decode_block(p.group, p.n_heads, p.H);
+  if (bc.b < 0) return;
+  const int h = bc.h, b = bc.b;
   // causal: the last row blocks have the most keys -> schedule them first
-  const int qb = p.causal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;
+  const int qb = p.causal ? (p.n_blocks - 1 - bc.blk) : bc.blk;
   const int q_row0 = qb * 2 * kBM;
   const int n_kv_all = (p.Nk + kBN - 1) / kBN;
   // KV tiles each Q tile needs (0 = tile entirely past N)
@@ -141,8 +146,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   const int nmax = max(n_t[0], n_t[1]);
 #ifdef FA_FWD_TRACE
   // SM clock under load: cycles and nanoseconds over the life of the last CTA in launch order
-  if (p.prof != nullptr && threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 &&
-      blockIdx.z == gridDim.z - 1) {
+  if (p.prof != nullptr && threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1) {
     unsigned long long ns;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
     p.prof[256] = clock64();
@@ -423,8 +427,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     tmem_dealloc(tmem_base, 512);
   }
 #ifdef FA_FWD_TRACE
-  if (p.prof != nullptr && threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 &&
-      blockIdx.z == gridDim.z - 1) {
+  if (p.prof != nullptr && threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1) {
     unsigned long long ns;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
     p.prof[258] = clock64();
@@ -442,8 +445,12 @@ int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUt
     FA_CUDA_CHECK(cudaFuncSetAttribute(fwd_tc_kernel<D, IS_BF16>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   }
-  dim3 grid((p.Nq + 2 * kBM - 1) / (2 * kBM), p.H, B);
-  fwd_tc_kernel<D, IS_BF16><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, p);
+  FwdParams q = p;
+  q.n_blocks = (p.Nq + 2 * kBM - 1) / (2 * kBM);
+  q.n_heads = B * p.H;
+  q.group = dispatch_group(p.causal != 0, (int64_t)2 * p.Nk * D * 2, q.n_heads);
+  if (q.n_blocks > 65535) q.group = 1;  // grid.y limit of the grouped form
+  fwd_tc_kernel<D, IS_BF16><<<dispatch_grid(q.group, q.n_blocks, p.H, B), kThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, q);
   FA_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return FA_OK;
