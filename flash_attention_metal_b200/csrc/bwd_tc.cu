@@ -208,7 +208,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     mbar_init(acc_full, 1);
     mbar_init(x_full, 1);
     mbar_init(y_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 256); mbar_init(&ds_ready[i], 256); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 8 * kArrivalsPerWarp); mbar_init(&ds_ready[i], 8 * kArrivalsPerWarp); }
     for (int i = 0; i < Cfg::kQSlots; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < Cfg::kDoSlots; ++i) { mbar_init(&do_full[i], 1); mbar_init(&do_empty[i], 1); }
     fence_barrier_init();
@@ -230,21 +230,30 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int key = key0 + tid;
     // per-column statistics (-L_i * log2e for threads 0-63, -D_i * scale for threads 64-127) of the 64
     // query columns this warpgroup owns, fetched one tile ahead
+    // The load is issued one tile ahead and its value is only touched (scaled) at the top of the
+    // next iteration: any arithmetic on it here would stall this in-order warp for the full global
+    // load latency every tile (measured: ~500 of 2700 cycles per tile).
+    const float *stat_src = (tid < 64 ? p.L : p.delta) + vec_off + wg * 64 + (tid & 63);
+    const float stat_coef = tid < 64 ? -kLog2e : -p.scale;
     auto fetch_stat = [&](int i) -> float {
-      const int qi = (i_start + i) * 128 + wg * 64 + (tid & 63);
-      if (i >= n || qi >= p.Nq) return tid < 64 ? -CUDART_INF_F : 0.f;
-      return tid < 64 ? -__ldg(p.L + vec_off + qi) * kLog2e : -__ldg(p.delta + vec_off + qi) * p.scale;
+      const int q_first = (i_start + i) * 128;
+      float v = tid < 64 ? CUDART_INF_F : 0.f;  // rows past N: P = exp2(-inf) = 0, D = 0
+      if (i < n && q_first + wg * 64 + (tid & 63) < p.Nq) v = __ldg(stat_src + q_first);
+      return v;
     };
     float stat_next = fetch_stat(0);
     const uint64_t scale_log2_2 = pack_f32x2(p.scale_log2, p.scale_log2), scale_2 = pack_f32x2(p.scale, p.scale);
     const bool prof = p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
-    long long tw_x = 0, t_p1 = 0, tw_y = 0, t_p2 = 0, t_begin = prof ? clock64() : 0;
+    long long tw_x = 0, t_p1 = 0, tw_y = 0, t_p2 = 0, t_top = 0, t_top2 = 0, t_begin = prof ? clock64() : 0;
     for (int i = 0; i < n; ++i) {
       const int q0 = (i_start + i) * 128 + wg * 64;  // first query column of this warpgroup's half
       float *ld = sLD + (wg * 2 + (i & 1)) * 128;
-      ld[tid] = stat_next;
+      long long ca = prof ? clock64() : 0;
+      ld[tid] = stat_next * stat_coef;
+      long long cb = prof ? clock64() : 0;
       stat_next = fetch_stat(i + 1);
       named_bar_sync(1 + wg, 128);
+      if (prof) { t_top += cb - ca; t_top2 += clock64() - cb; }
       // ---- phase 1: P^T = exp2(S^T * c - L * log2e) ----
       long long c0 = prof ? clock64() : 0;
       mbar_wait(x_full, i & 1);
@@ -292,7 +301,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (kDkdvParts == 2 || c == 1) {
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&p_ready[kDkdvParts == 2 ? c : 0]);
+          mbar_arrive_warp(&p_ready[kDkdvParts == 2 ? c : 0]);
         }
       }
       // ---- phase 2: dS^T = P^T o (dP^T * scale - D * scale) ----
@@ -320,14 +329,14 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (kDkdvParts == 2 || c == 1) {
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&ds_ready[kDkdvParts == 2 ? c : 0]);
+          mbar_arrive_warp(&ds_ready[kDkdvParts == 2 ? c : 0]);
         }
       }
       if (prof) { tw_x += c1 - c0; t_p1 += c2 - c1; tw_y += c3 - c2; t_p2 += clock64() - c3; }
     }
     if (prof) {
       long long *o = p.prof + wg * 8;
-      o[0] = n; o[1] = tw_x; o[2] = t_p1; o[3] = tw_y; o[4] = t_p2; o[5] = clock64() - t_begin;
+      o[0] = n; o[1] = tw_x; o[2] = t_p1; o[3] = tw_y; o[4] = t_p2; o[5] = clock64() - t_begin; o[6] = t_top; o[7] = t_top2;
     }
     // ------------------------------ epilogue ------------------------------
     mbar_wait(acc_full, 0);
@@ -508,8 +517,8 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int i = 0; i < 2; ++i) {
       mbar_init(&res_full[i], 1); mbar_init(&acc_full[i], 1);
       mbar_init(&x_full[i], 1); mbar_init(&y_full[i], 1);
-      mbar_init(&x_taken[i], 128);
-      for (int c = 0; c < 4; ++c) mbar_init(&ds_ready[4 * i + c], 128);
+      mbar_init(&x_taken[i], 4 * kArrivalsPerWarp);
+      for (int c = 0; c < 4; ++c) mbar_init(&ds_ready[4 * i + c], 4 * kArrivalsPerWarp);
     }
     for (int i = 0; i < Cfg::kKSlots; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < Cfg::kVSlots; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
@@ -544,7 +553,7 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       for (int c = 0; c < 4; ++c) tmem_ld32(tX + c * 32, pr[c]);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(&x_taken[t]);
+      mbar_arrive_warp(&x_taken[t]);
       const int k0 = s * 128;
       const bool diag = p.causal && (s == nt - 1);
       if (!diag) {
@@ -588,7 +597,7 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if (kDqParts == 4 || c == 3) {
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&ds_ready[4 * t + (kDqParts == 4 ? c : 0)]);
+          mbar_arrive_warp(&ds_ready[4 * t + (kDqParts == 4 ? c : 0)]);
         }
       }
     }

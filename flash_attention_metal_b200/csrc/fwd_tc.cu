@@ -158,7 +158,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
       mbar_init(&s_full[i], 1);
-      for (int q = 0; q < 4; ++q) mbar_init(&p_full[4 * i + q], kBM);
+      for (int q = 0; q < 4; ++q) mbar_init(&p_full[4 * i + q], 4 * kArrivalsPerWarp);
       mbar_init(&o_full[i], 1);
     }
     for (int i = 0; i < Cfg::kStages; ++i) {
@@ -279,7 +279,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         if ((c + 1) % (4 / kParts) == 0) {
           tmem_wait_st();
           tc_fence_before();
-          mbar_arrive(&p_full[4 * t + (c + 1) / (4 / kParts) - 1]);
+          mbar_arrive_warp(&p_full[4 * t + (c + 1) / (4 / kParts) - 1]);
           FA_TRACE((warp & 3) == 0 && lane == 0, j, t * 5 + 3 + (c == 3));
         }
       }

@@ -17,7 +17,7 @@ for (B, H, n, d, causal) in [(1, 16, 16384, 128, False), (1, 16, 16384, 128, Tru
     L.fa_debug_set_prof_buffer(prof.data_ptr()); run(); torch.cuda.synchronize(); L.fa_debug_set_prof_buffer(None)
     p = prof.cpu().tolist()
     for wg in (0, 1):
-        nt, wx, p1, wy, p2, tot = p[8 * wg:8 * wg + 6]
-        print(f"dkdv N={n} causal={int(causal)} WG{wg}: tiles {nt}  wait X {wx/nt:.0f}  phase1 {p1/nt:.0f}  wait Y {wy/nt:.0f}  phase2 {p2/nt:.0f}  total/tile {tot/nt:.0f}")
+        nt, wx, p1, wy, p2, tot, top, top2 = p[8 * wg:8 * wg + 8]
+        print(f"dkdv N={n} causal={int(causal)} WG{wg}: tiles {nt}  wait X {wx/nt:.0f}  phase1 {p1/nt:.0f}  wait Y {wy/nt:.0f}  phase2 {p2/nt:.0f}  total/tile {tot/nt:.0f}  [stat store {top/nt:.0f}, fetch+barrier {top2/nt:.0f}]")
     nt = p[0]
     print(f"   MMA thread: wait P {p[16]/nt:.0f}  wait dS {p[17]/nt:.0f}  loop/tile {p[18]/nt:.0f}  (MMA work per tile 2048 cycles)")
