@@ -65,6 +65,19 @@ __device__ __forceinline__ uint64_t exp2_pair(uint64_t x2, bool emulate) {
   return emulate ? exp2_emulated_x2(x2) : pack_f32x2(ex2(lo_f32(x2)), ex2(hi_f32(x2)));
 }
 
+// FA_BWD_TRACE (development builds only): the first dQ CTA records clock64() timestamps of its
+// hand-offs for items s = 8..11 of both tiles into the buffer set with fa_debug_set_prof_buffer.
+#ifdef FA_BWD_TRACE
+#define FA_BTRACE(cond, s_, slot)                                                                \
+  do {                                                                                           \
+    if (p.prof != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (cond) &&  \
+        (s_) >= 8 && (s_) < 12)                                                                  \
+      p.prof[64 + ((s_) - 8) * 64 + (slot)] = clock64();                                         \
+  } while (0)
+#else
+#define FA_BTRACE(cond, s_, slot) do {} while (0)
+#endif
+
 struct BwdParams {
   const float *L;      // [B, H, N] log-sum-exp of the scaled scores (natural log)
   const float *delta;  // [B, H, N] D_i (workspace)
@@ -548,12 +561,14 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       // ---- phase 1: copy S out (frees X for the other tile), P = exp2(S * c - L * log2e) ----
       mbar_wait(&x_full[t], s & 1);
       tc_fence_after();
+      FA_BTRACE(tid == 0, s, t * 8 + 0);
       uint32_t pr[4][32];
 #pragma unroll
       for (int c = 0; c < 4; ++c) tmem_ld32(tX + c * 32, pr[c]);
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive_warp(&x_taken[t]);
+      FA_BTRACE(tid == 0, s, t * 8 + 1);
       const int k0 = s * 128;
       const bool diag = p.causal && (s == nt - 1);
       if (!diag) {
@@ -580,8 +595,10 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
       }
       // ---- phase 2: dS = P o (dP * scale - D * scale), 16-bit, over the first half of Y ----
+      FA_BTRACE(tid == 0, s, t * 8 + 2);
       mbar_wait(&y_full[t], s & 1);
       tc_fence_after();
+      FA_BTRACE(tid == 0, s, t * 8 + 3);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t y[32], dk[16];
@@ -598,6 +615,7 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           tmem_wait_st();
           tc_fence_before();
           mbar_arrive_warp(&ds_ready[4 * t + (kDqParts == 4 ? c : 0)]);
+          FA_BTRACE(tid == 0 && (c == 0 || c == 3), s, t * 8 + 4 + (c == 3));
         }
       }
     }
@@ -682,7 +700,9 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
           for (int kk = 0; kk < D / 16; ++kk)
             mma_ss(tY, kmajor_desc(do_a, kk), kmajor_desc(v_addr(s), kk), idesc_xy, kk > 0);
+          FA_BTRACE(true, s, 32 + t);
           tc_commit(&y_full[t]);
+          FA_BTRACE(true, s, 34 + t);
           // last use of V_s: release its slot once this MMA has completed
           if (k + 1 >= n_items || item_s(k + 1) != s) tc_commit(&v_empty[s % Cfg::kVSlots]);
         };
@@ -692,14 +712,18 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         }
         for (int k = 0; k < n_items; ++k) {
           const int s = item_s(k), t = item_t(k);
+          FA_BTRACE(true, s, 16 + t * 8 + 0);
           if (k + 1 < n_items) {
             mbar_wait(&x_taken[t], s & 1);  // X is free again
+            FA_BTRACE(true, s, 16 + t * 8 + 1);
             issue_x(k + 1);
+            FA_BTRACE(true, s, 16 + t * 8 + 2);
           }
 #pragma unroll
           for (int part = 0; part < kDqParts; ++part) {  // dQ_t += dS K_s   (K = 128 keys)
             mbar_wait(&ds_ready[4 * t + part], s & 1);
             tc_fence_after();
+            FA_BTRACE(part == 0 || part == kDqParts - 1, s, 16 + t * 8 + 3 + (part > 0));
 #pragma unroll
             for (int kk = part * (8 / kDqParts); kk < (part + 1) * (8 / kDqParts); ++kk)
               mma_ts(tmem_base + 256 + t * D, tY + kk * 8, mnmajor_desc(k_addr(s), kk), idesc_acc,
@@ -707,7 +731,9 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           }
           if (s == n_t[t] - 1) tc_commit(&acc_full[t]);
           if (k + 1 >= n_items || item_s(k + 1) != s) tc_commit(&k_empty[s % Cfg::kKSlots]);
+          FA_BTRACE(true, s, 16 + t * 8 + 5);
           if (k + 1 < n_items) issue_y(k + 1);
+          FA_BTRACE(true, s, 16 + t * 8 + 6);
         }
       }
       __syncwarp();
