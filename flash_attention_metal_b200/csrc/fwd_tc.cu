@@ -104,6 +104,7 @@ struct FwdParams {
   int64_t batch_stride, head_stride;  // elements, of Q / O
   int causal;         // requires Nq == Nk
   int group, n_blocks, n_heads;  // dispatch order (sched.cuh)
+  int split;          // CTAs per cluster that share one row block, each taking 1/split of the keys
 };
 
 template <int D, int IS_BF16>
@@ -133,7 +134,13 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   if (bc.b < 0) return;
   const int h = bc.h, b = bc.b;
   // causal: the last row blocks have the most keys -> schedule them first
-  const int qb = p.causal ? (p.n_blocks - 1 - bc.blk) : bc.blk;
+  // Small launches (fewer row blocks than half the SMs) run split = 2, 4 or 8: a cluster of CTAs
+  // works on one row block, each on its share of the key tiles; the partial (m, l, O) results are
+  // merged through distributed shared memory by the online-softmax rule (see the epilogue).
+  const int split = p.split;
+  const int crank = split > 1 ? (int)cluster_ctarank() : 0;
+  const int blk = split > 1 ? bc.blk / split : bc.blk;
+  const int qb = p.causal ? (p.n_blocks - 1 - blk) : blk;
   const int q_row0 = qb * 2 * kBM;
   const int n_kv_all = (p.Nk + kBN - 1) / kBN;
   // KV tiles each Q tile needs (0 = tile entirely past N)
@@ -143,7 +150,13 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const int r0 = q_row0 + t * kBM;
     n_t[t] = r0 >= p.Nq ? 0 : (p.causal ? min(n_kv_all, r0 / kBN + 1) : n_kv_all);
   }
-  const int nmax = max(n_t[0], n_t[1]);
+  // this CTA's share of the key tiles: global tiles [j_begin, j_begin + c_t[t]) of Q tile t
+  const int n_all = max(n_t[0], n_t[1]);
+  const int j_begin = crank * n_all / split, j_end = (crank + 1) * n_all / split;
+  int c_t[2];
+#pragma unroll
+  for (int t = 0; t < 2; ++t) c_t[t] = max(0, min(j_end, n_t[t]) - j_begin);
+  const int nmax = max(c_t[0], c_t[1]);
 #ifdef FA_FWD_TRACE
   // SM clock under load: cycles and nanoseconds over the life of the last CTA in launch order
   if (p.prof != nullptr && threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1) {
@@ -185,7 +198,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     const uint32_t tS = tmem_base + lane_off + t * kBN;
     const uint32_t tO = tmem_base + lane_off + 256 + t * D;
     const int grow = q_row0 + t * kBM + row_in_tile;
-    const int nt = n_t[t];
+    const int nt = c_t[t];
     float m_run = -CUDART_INF_F;  // reference max (raw score units) the accumulators are relative to
     float l_run = 0.f;
 
@@ -200,11 +213,12 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       FA_TRACE((warp & 3) == 0 && lane == 0, j, t * 5 + 1);
 
       // ---- masks: causal diagonal tile (always the last one) / keys past N ----
-      const bool diag = p.causal && (j == nt - 1);
-      const bool tail = (j + 1) * kBN > p.Nk;
+      const int gj = j_begin + j;  // key tile index in the sequence
+      const bool diag = p.causal && (gj == n_t[t] - 1);
+      const bool tail = (gj + 1) * kBN > p.Nk;
       if (diag || tail) {
-        int limit = p.Nk - 1 - j * kBN;                 // last valid key column in this tile
-        if (diag) limit = min(limit, grow - j * kBN);  // key <= query row
+        int limit = p.Nk - 1 - gj * kBN;                 // last valid key column in this tile
+        if (diag) limit = min(limit, grow - gj * kBN);  // key <= query row
 #pragma unroll
         for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -287,30 +301,121 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       l_run = l_run * acc_scale + (lo_f32(st2) + hi_f32(st2));
     }
 
-    if (nt > 0) {
-      // ------------------------------ epilogue -------------------------------
-      mbar_wait(&o_full[t], 0);
-      tc_fence_after();
-      const float inv_l = 1.f / l_run;
-      const int64_t head_off = (int64_t)b * p.batch_stride + (int64_t)h * p.head_stride;
-      uint16_t *orow = reinterpret_cast<uint16_t *>(p.O) + head_off + (int64_t)grow * D;
+    if (split == 1) {
+      if (nt > 0) {
+        // ------------------------------ epilogue -------------------------------
+        mbar_wait(&o_full[t], 0);
+        tc_fence_after();
+        const float inv_l = 1.f / l_run;
+        const int64_t head_off = (int64_t)b * p.batch_stride + (int64_t)h * p.head_stride;
+        uint16_t *orow = reinterpret_cast<uint16_t *>(p.O) + head_off + (int64_t)grow * D;
+  #pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tO + c * 32, o);
+          tmem_wait_ld();
+          uint32_t w[16];
+  #pragma unroll
+          for (int i = 0; i < 16; ++i)
+            w[i] = pack2<IS_BF16>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+          if (grow < p.Nq) {
+            uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
+  #pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          }
+        }
+        if (p.L != nullptr && grow < p.Nq)
+          p.L[head_off / D + grow] = m_run * p.scale + lg2(l_run) * kLn2;
+      }
+    } else {
+      // ------------------------- epilogue of a key split ----------------------
+      // Binary tree over the cluster ranks: in round `step` rank r + step sends its partial
+      // (m, l, unnormalised O) to rank r (r a multiple of 2 * step) through distributed shared
+      // memory; the receiver merges by the online-softmax rule and keeps the result in its own
+      // TMEM accumulator; after the last round rank 0 normalises and stores.
+      if (nt > 0) {
+        mbar_wait(&o_full[t], 0);
+        tc_fence_after();
+      }
+      float *xO = reinterpret_cast<float *>(sKV);  // [tile][column][row]: conflict-free both ways
+      float *xM = reinterpret_cast<float *>(sQ);   // [tile][row]
+      float *xL = xM + 2 * kBM;
+      float m_cur = nt > 0 ? m_run : -CUDART_INF_F, l_cur = nt > 0 ? l_run : 0.f;
+      bool o_valid = nt > 0;  // my TMEM accumulator holds data
+      for (int step = 1; step < split; step *= 2) {
+        const bool sender = (crank & (2 * step - 1)) == step, receiver = (crank & (2 * step - 1)) == 0;
+        cluster_arrive();  // the receivers' K/V stages and Q tiles are dead (tile loop over, or the
+        cluster_wait();    // previous round has been read) and can take a partial result
+        if (sender) {
+          const uint32_t dst = (uint32_t)(crank - step);
+          const uint32_t rO = mapa_shared(smem_u32(xO), dst), rM = mapa_shared(smem_u32(xM), dst),
+                         rL = mapa_shared(smem_u32(xL), dst);
+          st_cluster_f32(rM + (t * kBM + row_in_tile) * 4, m_cur);
+          st_cluster_f32(rL + (t * kBM + row_in_tile) * 4, l_cur);
 #pragma unroll
-      for (int c = 0; c < D / 32; ++c) {
-        uint32_t o[32];
-        tmem_ld32(tO + c * 32, o);
-        tmem_wait_ld();
-        uint32_t w[16];
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            if (o_valid) {
+              tmem_ld32(tO + c * 32, o);
+              tmem_wait_ld();
+            } else {
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          w[i] = pack2<IS_BF16>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
-        if (grow < p.Nq) {
-          uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
+              for (int i = 0; i < 32; ++i) o[i] = 0u;
+            }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            for (int i = 0; i < 32; ++i)
+              st_cluster_f32(rO + ((t * D + c * 32 + i) * kBM + row_in_tile) * 4, __uint_as_float(o[i]));
+          }
+        }
+        cluster_arrive();  // the senders' stores are visible to the receivers
+        cluster_wait();
+        if (receiver) {
+          const float m_b = xM[t * kBM + row_in_tile], l_b = xL[t * kBM + row_in_tile];
+          const float m = fmaxf(m_cur, m_b);
+          const float w_a = m_cur == -CUDART_INF_F ? 0.f : ex2((m_cur - m) * p.scale_log2);
+          const float w_b = m_b == -CUDART_INF_F ? 0.f : ex2((m_b - m) * p.scale_log2);
+#pragma unroll
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            if (o_valid) {
+              tmem_ld32(tO + c * 32, o);
+              tmem_wait_ld();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = 0u;
+            }
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              o[i] = __float_as_uint(__uint_as_float(o[i]) * w_a + xO[(t * D + c * 32 + i) * kBM + row_in_tile] * w_b);
+            tmem_st32(tO + c * 32, o);
+          }
+          tmem_wait_st();
+          l_cur = l_cur * w_a + l_b * w_b;
+          m_cur = m;
+          o_valid = true;
         }
       }
-      if (p.L != nullptr && grow < p.Nq)
-        p.L[head_off / D + grow] = m_run * p.scale + lg2(l_run) * kLn2;
+      if (crank == 0 && n_t[t] > 0) {
+        const float inv_l = 1.f / l_cur;
+        const int64_t head_off = (int64_t)b * p.batch_stride + (int64_t)h * p.head_stride;
+        uint16_t *orow = reinterpret_cast<uint16_t *>(p.O) + head_off + (int64_t)grow * D;
+#pragma unroll
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tO + c * 32, o);
+          tmem_wait_ld();
+          uint32_t w[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            w[i] = pack2<IS_BF16>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
+          if (grow < p.Nq) {
+            uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          }
+        }
+        if (p.L != nullptr && grow < p.Nq) p.L[head_off / D + grow] = m_cur * p.scale + lg2(l_cur) * kLn2;
+      }
     }
   } else {
     setmaxnreg_dec<64>();
@@ -322,7 +427,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         prefetch_tensormap(&tmV);
 #pragma unroll
         for (int t = 0; t < 2; ++t)
-          if (n_t[t] > 0) {
+          if (c_t[t] > 0) {
             mbar_arrive_expect_tx(&q_full[t], Cfg::kTileBytes);
 #pragma unroll
             for (int c = 0; c < Cfg::kChunks; ++c)
@@ -339,13 +444,13 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
           for (int c = 0; c < Cfg::kChunks; ++c)
             tma_load_4d(sKV + stage * Cfg::kTileBytes + c * Cfg::kChunkBytes, map, &kv_full[stage],
-                        c * 64, (item >> 1) * kBN, h, b);
+                        c * 64, (j_begin + (item >> 1)) * kBN, h, b);
         }
       }
       __syncwarp();
     } else if (warp == kMmaWarp) {
       // =============================== MMA issuer ===============================
-      if (elect_one()) {
+      if (nmax > 0 && elect_one()) {  // (a rank of a key split can be left without tiles on short causal rows)
         constexpr uint32_t idesc_qk = make_idesc(kBM, kBN, IS_BF16, 0, 0);
         constexpr uint32_t idesc_pv = make_idesc(kBM, D, IS_BF16, 0, 1);
         const uint32_t sQ_addr = smem_u32(sQ);
@@ -379,7 +484,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
         const uint32_t ks0 = wait_full(0);
 #pragma unroll
         for (int t = 0; t < 2; ++t)
-          if (n_t[t] > 0) {
+          if (c_t[t] > 0) {
             mbar_wait(&q_full[t], 0);
             tc_fence_after();
             issue_qk(t, ks0);
@@ -395,7 +500,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           FA_TRACE(true, j, 20);
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
-            if (j < n_t[t]) {
+            if (j < c_t[t]) {
 #pragma unroll
               for (int part = 0; part < kParts; ++part) {
                 mbar_wait(&p_full[4 * t + part], j & 1);
@@ -404,9 +509,9 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
                 issue_pv(t, part, vs, j > 0);
               }
               FA_TRACE(true, j, 23 + t * 5);
-              if (j == n_t[t] - 1) tc_commit(&o_full[t]);
+              if (j == c_t[t] - 1) tc_commit(&o_full[t]);
             }
-            if (j + 1 < n_t[t]) {
+            if (j + 1 < c_t[t]) {
               issue_qk(t, ks);
               tc_commit(&s_full[t]);
               FA_TRACE(true, j, 25 + t * 5);
@@ -420,6 +525,14 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     }
   }
 
+  if (split > 1 && warp >= 8) {  // the cluster barriers of the split epilogue are for every thread
+    for (int step = 1; step < split; step *= 2) {
+      cluster_arrive();
+      cluster_wait();
+      cluster_arrive();
+      cluster_wait();
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
@@ -450,7 +563,38 @@ int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUt
   q.n_heads = B * p.H;
   q.group = dispatch_group(p.causal != 0, (int64_t)2 * p.Nk * D * 2, q.n_heads);
   if (q.n_blocks > 65535) q.group = 1;  // grid.y limit of the grouped form
-  fwd_tc_kernel<D, IS_BF16><<<dispatch_grid(q.group, q.n_blocks, p.H, B), kThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, q);
+  // fewer row blocks than half the SMs: several CTAs (one cluster) per row block, splitting the keys
+  int n_sm = 148;
+  {
+    static int sm_count[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+      if (sm_count[dev] == 0) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
+      if (sm_count[dev] > 0) n_sm = sm_count[dev];
+    }
+  }
+  // largest power of two (cluster size <= 8) that still fits one wave and leaves every rank at
+  // least two key tiles of the longest row
+  q.split = 1;
+  while (q.split < 8 && 2 * q.split * q.n_blocks * q.n_heads <= n_sm && (p.Nk + kBN - 1) / kBN >= 4 * q.split) q.split *= 2;
+  if (q.split > 1) {
+    q.group = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(q.n_blocks * q.split), (unsigned)p.H, (unsigned)B);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)q.split;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fwd_tc_kernel<D, IS_BF16>, tmQ, tmK, tmV, q));
+  } else {
+    fwd_tc_kernel<D, IS_BF16><<<dispatch_grid(q.group, q.n_blocks, p.H, B), kThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, q);
+  }
   FA_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return FA_OK;

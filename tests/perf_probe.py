@@ -30,6 +30,15 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "d64":
     bench(1, 16, 16384, 128, True)
     bench(1, 16, 16384, 128, False)
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "small":
+    for n in (512, 1024, 2048, 4096, 8192, 16384):
+        bench(1, 1, n, 64, False, fa.FP16)
+    for n in (1024, 4096, 16384):
+        bench(1, 1, n, 64, True)
+        bench(1, 1, n, 128, True)
+    bench(1, 4, 4096, 128, True)
+    bench(2, 8, 2048, 64, True)
+
 if __name__ == "__main__" and len(sys.argv) == 1:
     bench(1, 16, 16384, 128, True)
     bench(1, 16, 16384, 128, False)

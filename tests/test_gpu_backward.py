@@ -233,3 +233,32 @@ def test_no_writes_outside_the_output_tensors(fa):
             assert bool((buf[:guard] == fill).all()) and bool((buf[-guard:] == fill).all()), (n, d)
         assert torch.isfinite(O.view(torch.bfloat16).float()).all()
         assert all(torch.isfinite(g[1]).all() for g in gb)
+
+
+def test_backward_gpt2_shape_all_heads(fa):
+    """BASELINE config 4 (bf16, B=8, H=12, N=4096, d=64, causal): dQ, dK, dV of every head against
+    dense fp64 math (the formulas of oracle_backward / main.mm:1091-1179 with the causal mask)."""
+    import torch
+
+    B, H, n, d = 8, 12, 4096, 64
+    scale = float(1.0 / np.sqrt(d))
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    Q, K, V, dO = (torch.rand((B, H, n, d), device="cuda", generator=gen).mul_(2).sub_(1).to(torch.bfloat16) for _ in range(4))
+    O = torch.empty_like(Q)
+    L = torch.empty((B, H, n), device="cuda")
+    fa.flash_attention_v4_half(Q, K, V, O, n, d, scale, H * n * d, n * d, L, True, B, H, fa.BF16)
+    dQ, dK, dV = (torch.empty((B, H, n, d), device="cuda") for _ in range(3))
+    wsb = fa.workspace_bytes_backward(n, d, B, H)
+    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+    fa.flash_attention_backward(Q, K, V, O, dO, L, dQ, dK, dV, n, d, scale, H * n * d, n * d, True, B, H, fa.BF16, ws, wsb)
+    torch.cuda.synchronize()
+    mask = torch.ones(n, n, dtype=torch.bool, device="cuda").triu(1)
+    for b in range(B):
+        for h in range(H):
+            q, k, v, do = (t[b, h].double() for t in (Q, K, V, dO))
+            p = torch.softmax(((q @ k.T) * scale).masked_fill(mask, float("-inf")), dim=1)
+            dp = do @ v.T
+            ds = p * (dp - (dp * p).sum(1, keepdim=True)) * scale
+            for got, want in ((dQ[b, h], ds @ k), (dK[b, h], ds.T @ q), (dV[b, h], p.T @ do)):
+                err = (got.double() - want).abs().max().item()
+                assert err <= TOL_ABS and err <= TOL_REL[oracle.BF16] * want.abs().max().item(), (b, h, err)

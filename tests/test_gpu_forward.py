@@ -270,3 +270,66 @@ def test_flagship_shape_sampled_rows(fa, causal):
             assert abs(L[0, h, i].item() - lse.item()) <= TOL_LSE
     if causal:
         assert torch.equal(O[0, :, 0], V[0, :, 0])
+
+
+def _dense_reference(Q, K, V, scale, causal):
+    """fp64 dense attention of one head on the GPU (same formulas as the oracle's forward:
+    oracle/cpu_ref.c oracle_forward / main.mm:128-159, 549-578), used where the CPU oracle cannot
+    finish: it is first checked against the oracle itself in test_dense_reference_matches_oracle."""
+    torch = _torch()
+    s = (Q.double() @ K.double().T) * scale
+    if causal:
+        n = s.shape[0]
+        s = s.masked_fill(torch.ones(n, n, dtype=torch.bool, device=s.device).triu(1), float("-inf"))
+    return torch.softmax(s, dim=1) @ V.double(), torch.logsumexp(s, dim=1)
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_dense_reference_matches_oracle(fa, causal):
+    n, d, scale = 256, 64, 0.125
+    q, k, v = indep_inputs(n, d)
+    want, want_l = oracle.forward(q, k, v, scale, causal)
+    got, got_l = _dense_reference(dev(q), dev(k), dev(v), scale, causal)
+    assert np.abs(got.cpu().numpy() - want).max() <= 2e-6
+    assert np.abs(got_l.cpu().numpy() - want_l).max() <= 2e-5
+
+
+@pytest.mark.parametrize("causal", [True, False])
+def test_flagship_shape_full_heads(fa, causal):
+    """BASELINE config 3 (bf16, B=1, H=16, N=16384, d=128): every row of two heads against the dense
+    fp64 reference."""
+    torch = _torch()
+    B, H, n, d = 1, 16, 16384, 128
+    scale = float(1.0 / np.sqrt(d))
+    g = torch.Generator(device="cuda").manual_seed(99)
+    Q, K, V = (torch.rand((B, H, n, d), device="cuda", generator=g).mul_(2).sub_(1).to(torch.bfloat16) for _ in range(3))
+    O = torch.empty_like(Q)
+    L = torch.empty((B, H, n), device="cuda")
+    fa.flash_attention_v4_half(Q, K, V, O, n, d, scale, H * n * d, n * d, L, causal, B, H, fa.BF16)
+    torch.cuda.synchronize()
+    for h in (3, 15):
+        want, want_l = _dense_reference(Q[0, h], K[0, h], V[0, h], scale, causal)
+        assert (O[0, h].double() - want).abs().max().item() <= TOL_HALF
+        assert (L[0, h].double() - want_l).abs().max().item() <= TOL_LSE
+        del want, want_l
+
+
+def test_gpt2_shape_all_heads(fa):
+    """BASELINE config 4 (bf16, B=8, H=12, N=4096, d=64, causal): every row of every head against
+    the dense fp64 reference."""
+    torch = _torch()
+    B, H, n, d = 8, 12, 4096, 64
+    scale = float(1.0 / np.sqrt(d))
+    g = torch.Generator(device="cuda").manual_seed(5)
+    Q, K, V = (torch.rand((B, H, n, d), device="cuda", generator=g).mul_(2).sub_(1).to(torch.bfloat16) for _ in range(3))
+    O = torch.empty_like(Q)
+    L = torch.empty((B, H, n), device="cuda")
+    fa.flash_attention_v4_half(Q, K, V, O, n, d, scale, H * n * d, n * d, L, True, B, H, fa.BF16)
+    torch.cuda.synchronize()
+    worst = 0.0
+    for b in range(B):
+        for h in range(H):
+            want, want_l = _dense_reference(Q[b, h], K[b, h], V[b, h], scale, True)
+            worst = max(worst, (O[b, h].double() - want).abs().max().item())
+            assert (L[b, h].double() - want_l).abs().max().item() <= TOL_LSE
+    assert worst <= TOL_HALF
