@@ -330,9 +330,14 @@ def run_ours(args):
                "pcie_gbs": (h2d + d2h) / (e_ms * 1e-3) / 1e9,
                "what": ("forward+backward" if have_bwd else "forward") + " through the host-buffer C-ABI call "
                        "(pinned host inputs -> device, kernels, every output -> host; copies pipelined over head groups)"}
-        assert torch.equal(ho.cuda(), O), "e2e forward result differs from the device-resident result"
+        # The host call runs the heads in groups; a small group takes the key-split forward (partial
+        # results merged in a different order), so the comparison with the all-heads device run is
+        # to one bf16 rounding step, not bitwise.  A misplaced head or copy would be O(1) off.
+        fo = (ho.cuda().float() - O.float()).abs().max().item()
+        assert fo <= 2.0 ** -8 * max(1.0, O.float().abs().max().item()), f"e2e forward result differs from the device-resident result by {fo}"
         if have_bwd:
-            assert torch.equal(hg[0].cuda(), dQ), "e2e dQ differs from the device-resident result"
+            gq = (hg[0].cuda() - dQ).abs().max().item()
+            assert gq <= 1e-2 * dQ.abs().max().item(), f"e2e dQ differs from the device-resident result by {gq}"
 
     if rank != 0:
         if world > 1:
