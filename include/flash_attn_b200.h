@@ -26,6 +26,12 @@
  *     strides (kernels.metal:608-609 uses int, which overflows at N = 1M);
  *     D in {64, 128} (reference: 64 only, main.mm:12); dtype = fp16 or bf16
  *     (reference: fp16 only).
+ *   - results are deterministic: the same call (same shapes, same device) returns
+ *     the same bits every time, forward and backward (the reference's backward
+ *     is not: float atomics, kernels.metal:1227, 1243).  They are not
+ *     bit-identical ACROSS call shapes: a 16-bit forward launch too small to
+ *     fill the GPU splits the keys of a row block over a thread-block cluster
+ *     and merges the parts, which sums in a different order than one CTA does.
  *
  * This header is plain C: no CUDA types appear in it.
  */
