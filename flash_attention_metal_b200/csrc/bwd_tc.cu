@@ -51,14 +51,18 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef FA_BWD_EMU
 #define FA_BWD_EMU 3
 #endif
+#ifndef FA_BWD_EMU_DQ
+#define FA_BWD_EMU_DQ FA_BWD_EMU
+#endif
 #ifndef FA_BWD_SPLIT
 #define FA_BWD_SPLIT 1
 #endif
 constexpr int kBwdEmu = FA_BWD_EMU;
 constexpr int kDkdvParts = FA_BWD_SPLIT ? 2 : 1;  // hand-offs per phase in bwd_dkdv_kernel
 constexpr int kDqParts = FA_BWD_SPLIT ? 4 : 1;    // dS hand-offs per item in bwd_dq_kernel
+template <int kEvery = kBwdEmu>
 __device__ __forceinline__ bool emulate_pair(int pair_index) {
-  return kBwdEmu > 0 && (pair_index % (kBwdEmu > 0 ? kBwdEmu : 1)) == (kBwdEmu > 0 ? kBwdEmu : 1) - 1;
+  return kEvery > 0 && (pair_index % (kEvery > 0 ? kEvery : 1)) == (kEvery > 0 ? kEvery : 1) - 1;
 }
 // 2^x of a packed pair: MUFU.EX2 or the FMA-pipe polynomial
 __device__ __forceinline__ uint64_t exp2_pair(uint64_t x2, bool emulate) {
@@ -577,7 +581,7 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
             const uint64_t x2 = fma_f32x2(pack_u32x2(pr[c][e], pr[c][e + 1]), scale_log2_2, neg_l2_2);
-            const uint64_t p2 = exp2_pair(x2, emulate_pair(e >> 1));
+            const uint64_t p2 = exp2_pair(x2, emulate_pair<FA_BWD_EMU_DQ>(e >> 1));
             pr[c][e] = __float_as_uint(lo_f32(p2));
             pr[c][e + 1] = __float_as_uint(hi_f32(p2));
           }

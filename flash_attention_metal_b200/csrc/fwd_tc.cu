@@ -167,6 +167,12 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   }
 #endif
 
+#ifdef FA_FWD_TRACE
+  if (p.prof != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    p.prof[260] = clock64();
+    p.prof[264] = nmax;
+  }
+#endif
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
@@ -205,6 +211,9 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
     for (int j = 0; j < nt; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
+#ifdef FA_FWD_TRACE
+      if (p.prof != nullptr && threadIdx.x == 0 && j == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.prof[261] = clock64();
+#endif
       FA_TRACE((warp & 3) == 0 && lane == 0, j, t * 5 + 0);
       uint32_t s[4][32];
 #pragma unroll
@@ -301,6 +310,9 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       l_run = l_run * acc_scale + (lo_f32(st2) + hi_f32(st2));
     }
 
+#ifdef FA_FWD_TRACE
+    if (p.prof != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.prof[262] = clock64();
+#endif
     if (split == 1) {
       if (nt > 0) {
         // ------------------------------ epilogue -------------------------------
@@ -535,6 +547,9 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+#ifdef FA_FWD_TRACE
+  if (p.prof != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.prof[263] = clock64();
+#endif
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);

@@ -73,6 +73,11 @@ def bench_bwd(B, H, n, d, causal, dtype=fa.BF16, reps=10):
     print(f"BWD B={B} H={H} N={n} d={d} causal={int(causal)}: median {ts[len(ts)//2]:.3f} ms -> {flop/ts[len(ts)//2]/1e9:.1f} TFLOP/s (5-GEMM accounting; hardware does 7)", flush=True)
 
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "bwd64":
+    bench_bwd(8, 12, 4096, 64, True)
+    bench_bwd(1, 16, 16384, 64, True)
+    bench_bwd(1, 16, 16384, 64, False)
+
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "bwd":
     bench_bwd(1, 16, 16384, 128, True)
     bench_bwd(1, 16, 16384, 128, False)

@@ -19,6 +19,9 @@ L.fa_debug_set_prof_buffer(None)
 p = prof.cpu().tolist()
 if p[259] > p[257]:
     print(f"SM clock under load (last CTA, {p[259] - p[257]} ns): {(p[258] - p[256]) / (p[259] - p[257]) * 1000:.0f} MHz")
+if p[263] > p[260]:
+    print(f"CTA (0,0,0): {p[264]} iterations; entry -> first S ready {p[261] - p[260]} cycles, tile loop {p[262] - p[261]}, "
+          f"epilogue (last P published -> all warps done) {p[263] - p[262]}")
 p = p[:256]
 names = {}
 for t in (0, 1):
