@@ -592,20 +592,41 @@ int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUt
   // least two key tiles of the longest row
   q.split = 1;
   while (q.split < 8 && 2 * q.split * q.n_blocks * q.n_heads <= n_sm && (p.Nk + kBN - 1) / kBN >= 4 * q.split) q.split *= 2;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
   if (q.split > 1) {
-    q.group = 1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(q.n_blocks * q.split), (unsigned)p.H, (unsigned)B);
+    // largest cluster of these one-CTA-per-SM blocks the device can co-schedule (asked once per device)
+    static int max_cluster[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)q.split;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (max_cluster[dev] == 0) {
+      int best = 1;
+      for (int c = 8; c > 1; c /= 2) {
+        int n_clusters = 0;
+        cfg.gridDim = dim3((unsigned)c, 1, 1);
+        attr[0].val.clusterDim.x = (unsigned)c;
+        if (cudaOccupancyMaxActiveClusters(&n_clusters, fwd_tc_kernel<D, IS_BF16>, &cfg) == cudaSuccess && n_clusters > 0) {
+          best = c;
+          break;
+        }
+        (void)cudaGetLastError();
+      }
+      max_cluster[dev] = best;
+    }
+    if (q.split > max_cluster[dev]) q.split = max_cluster[dev];
+  }
+  if (q.split > 1) {
+    q.group = 1;
+    cfg.gridDim = dim3((unsigned)(q.n_blocks * q.split), (unsigned)p.H, (unsigned)B);
+    attr[0].val.clusterDim.x = (unsigned)q.split;
     FA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fwd_tc_kernel<D, IS_BF16>, tmQ, tmK, tmV, q));
   } else {
     fwd_tc_kernel<D, IS_BF16><<<dispatch_grid(q.group, q.n_blocks, p.H, B), kThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, q);
