@@ -588,10 +588,13 @@ int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUt
       if (sm_count[dev] > 0) n_sm = sm_count[dev];
     }
   }
-  // largest power of two (cluster size <= 8) that still fits one wave and leaves every rank at
-  // least two key tiles of the longest row
+  // largest power of two that still fits one wave and leaves every rank at least four key tiles of
+  // the longest row.  Clusters of 8 work (FA_FWD_SPLIT_MAX=8) but measured slower than 4 (single
+  // head N=4096: 56 us unsplit, 37 / 28 / 42 us at 2 / 4 / 8: a third merge round, and eight
+  // whole-SM CTAs have to be co-scheduled in one GPC).
   q.split = 1;
-  while (q.split < 8 && 2 * q.split * q.n_blocks * q.n_heads <= n_sm && (p.Nk + kBN - 1) / kBN >= 4 * q.split) q.split *= 2;
+  static const int split_cap = [] { const char *e = getenv("FA_FWD_SPLIT_MAX"); return e ? atoi(e) : 4; }();
+  while (q.split < split_cap && 2 * q.split * q.n_blocks * q.n_heads <= n_sm && (p.Nk + kBN - 1) / kBN >= 4 * q.split) q.split *= 2;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   if (q.split > 1) {

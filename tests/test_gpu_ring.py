@@ -42,7 +42,8 @@ def rect_reference(q, k, v, scale):
 
 
 # the last three shapes launch fewer CTAs than half the SMs and many key tiles: the forward splits the
-# keys of each row block over clusters of 8 / 8 / 4 CTAs and merges through distributed shared memory
+# keys of each row block over a cluster of CTAs (4 by default; test_cluster_of_eight forces 8) and
+# merges the parts through distributed shared memory
 @pytest.mark.parametrize("nq,nk,d", [(128, 256, 64), (300, 77, 64), (64, 1000, 128), (513, 129, 128), (1, 5, 64),
                                      (200, 5000, 64), (130, 4500, 128), (700, 2100, 128)])
 def test_rectangular_forward(fa, nq, nk, d):
@@ -177,3 +178,16 @@ def test_rectangular_backward_blocks_sum_to_full_gradients(fa):
     fa.flash_attention_backward(Q, K, V, O, dO, L, *got, n, d, scale, n * d, n * d, False, 1, 1, fa.BF16, ws, wsb)
     for g, w in zip(got, want):
         assert np.abs(g.cpu().numpy() - w).max() <= 1e-2 * np.abs(w).max()
+
+
+def test_cluster_of_eight():
+    """The key split also works with clusters of 8 CTAs (not the default: measured slower than 4)."""
+    import subprocess, sys, os
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FA_FWD_SPLIT_MAX="8")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ring.py"), "-m", "gpu", "-q",
+                          "-k", "test_rectangular_forward"], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-1000:]
