@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include "fa_internal.h"
+#include "sched.cuh"
 
 namespace fa {
 
@@ -37,6 +38,14 @@ void fa_reset_launch_count(void) { g_launches = 0; }
 // Development aid (not in the public header): device buffer of >= 32 int64 that the backward dK/dV
 // kernel fills with phase timings of one CTA; pass NULL to switch it off.
 void fa_debug_set_prof_buffer(long long *dev) { g_fwd_prof = dev; }
+
+// Development aid (not in the public header): the dispatch geometry sched.cuh picks for a launch
+// of `n_blocks` blocks per head -- out = {heads per group, grid.x, grid.y, grid.z}.  Host logic only.
+void fa_debug_dispatch(int uneven_work, long long streamed_bytes_per_head, int n_blocks, int H, int B, int *out) {
+  const int group = dispatch_group(uneven_work != 0, streamed_bytes_per_head, H * B);
+  const dim3 g = dispatch_grid(group, n_blocks, H, B);
+  out[0] = group; out[1] = (int)g.x; out[2] = (int)g.y; out[3] = (int)g.z;
+}
 
 int fa_device_count(void) {
   int n = 0;
