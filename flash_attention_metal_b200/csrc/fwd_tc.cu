@@ -21,6 +21,13 @@
 // TMEM (512 columns): S0 [0,128) S1 [128,256) O0 [256,256+D) O1 [256+D,256+2D);
 // P_t aliases the first 64 columns of S_t (two 16-bit values per column).
 //
+// P is published to the MMA warp in parts (4 at D = 128, 2 at D = 64), one mbarrier each; one pair
+// of exponentials in four is computed on the FMA pipe (see the knobs below).
+//
+// Launch geometry (sched.cuh): heads in L2-sized groups, heaviest row blocks first.  Launches too
+// small to fill the GPU run as thread-block clusters of 2 or 4 CTAs per row block, each CTA on its
+// share of the key tiles, merged through distributed shared memory in the epilogue.
+//
 // Shared memory tiles are [128 rows][64 elements] boxes (128-byte rows, 128-byte
 // swizzle) exactly as TMA writes them: K-major operands for Q K^T (Q and K rows are
 // the M/N index, head dim is K), MN-major B operand for P V (V rows are the K index).
