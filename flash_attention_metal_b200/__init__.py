@@ -29,7 +29,7 @@ EXPORTS = (
     "fa_host_attention_fwd_bwd_half", "fa_host_release",
     "flash_attention_v4_half_rect", "fa_ring_unique_id_bytes", "fa_ring_get_unique_id", "fa_ring_create",
     "fa_ring_destroy", "fa_ring_workspace_bytes", "fa_ring_attention_forward", "fa_ring_plan", "fa_ring_local_rows",
-    "fa_ring_workspace_bytes_backward", "fa_ring_attention_backward",
+    "fa_ring_workspace_bytes_backward", "fa_ring_attention_backward", "fa_ring_workspace_bytes_gather",
     "fa_last_error", "fa_version", "fa_device_count", "fa_launch_count", "fa_reset_launch_count",
 )
 
@@ -79,6 +79,8 @@ def lib() -> C.CDLL:
         L.fa_ring_workspace_bytes.argtypes = [i32, i32, i32, i32]
         L.fa_ring_workspace_bytes.restype = sz
         L.fa_ring_attention_forward.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, i32, i32, vp, sz, vp]
+        L.fa_ring_workspace_bytes_gather.argtypes = [i32, i32, i32, i32, i32]
+        L.fa_ring_workspace_bytes_gather.restype = sz
         L.fa_ring_workspace_bytes_backward.argtypes = [i32, i32, i32, i32]
         L.fa_ring_workspace_bytes_backward.restype = sz
         L.fa_ring_attention_backward.argtypes = [vp] * 10 + [i32, i32, i32, f32, i32, i32, vp, sz, vp]
@@ -172,6 +174,10 @@ class Ring:
 
     def workspace_bytes(self, n_local, D, H, dtype) -> int:
         return int(lib().fa_ring_workspace_bytes(n_local, D, H, dtype))
+
+    def workspace_bytes_gather(self, world, n_local, D, H, dtype):
+        """Workspace of the all-gather forward mode (used when FA_RING_GATHER=1)."""
+        return int(lib().fa_ring_workspace_bytes_gather(world, n_local, D, H, dtype))
 
     def forward(self, Q, K, V, O, L_out, n_local, D, H, scale, is_causal, dtype, workspace, workspace_bytes, stream=None):
         _check(lib().fa_ring_attention_forward(self.handle, _ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(L_out), n_local, D,

@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math_constants.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "fa_internal.h"
@@ -34,6 +35,7 @@ struct NcclApi {
   int (*CommDestroy)(NcclComm);
   int (*Send)(const void *, size_t, int /*dtype*/, int, NcclComm, cudaStream_t);
   int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t);
+  int (*AllGather)(const void *, void *, size_t, int /*dtype*/, NcclComm, cudaStream_t);  // optional
   int (*GroupStart)();
   int (*GroupEnd)();
   const char *(*GetErrorString)(int);
@@ -58,6 +60,7 @@ NcclApi *nccl() {
       FA_SYM(CommDestroy, "ncclCommDestroy");
       FA_SYM(Send, "ncclSend");
       FA_SYM(Recv, "ncclRecv");
+      FA_SYM(AllGather, "ncclAllGather");
       FA_SYM(GroupStart, "ncclGroupStart");
       FA_SYM(GroupEnd, "ncclGroupEnd");
       FA_SYM(GetErrorString, "ncclGetErrorString");
@@ -286,6 +289,14 @@ size_t fa_ring_workspace_bytes(int n_local, int D, int H, int dtype) {
   return bytes + 1024;
 }
 
+// Workspace of the all-gather forward mode: room for every rank's K and V instead of two receive slots.
+size_t fa_ring_workspace_bytes_gather(int world, int n_local, int D, int H, int dtype) {
+  const size_t base = fa_ring_workspace_bytes(n_local, D, H, dtype);
+  if (base == 0 || world < 1) return 0;
+  const size_t tile = (size_t)H * n_local * D;
+  return base - 2 * (2 * tile * 2) + 2 * (size_t)world * tile * 2;
+}
+
 int fa_ring_attention_forward(void *ring, const void *Q, const void *K, const void *V, void *O, float *L_out,
                               int n_local, int D, int H, float scale, int is_causal, int dtype, void *workspace,
                               size_t workspace_bytes, fa_stream_t stream_) {
@@ -304,35 +315,29 @@ int fa_ring_attention_forward(void *ring, const void *Q, const void *K, const vo
   const size_t tile_elems = (size_t)H * n_local * D;
   const size_t tile_bytes = tile_elems * 2;
   char *ws = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
+  // All-gather mode (opt-in: FA_RING_GATHER=1 and a workspace of fa_ring_workspace_bytes_gather):
+  // for steps whose compute is shorter than their K/V hand-off (medium N on many GPUs) the ring is
+  // bound by its per-step transfer; here every rank's K/V is gathered once (ncclAllGather on the side
+  // stream, under the local block) and the P - 1 remote blocks then run back to back.
+  static const int gather_env = [] { const char *e = getenv("FA_RING_GATHER"); return e ? atoi(e) : 0; }();
+  const bool gather = gather_env != 0 && P > 1 && api->AllGather != nullptr &&
+                      workspace_bytes >= fa_ring_workspace_bytes_gather(P, n_local, D, H, dtype);
+  const size_t kv_area = gather ? 2 * (size_t)P * tile_bytes : 4 * tile_bytes;  // [K of all ranks | V of all ranks] or 2 slots
   char *slot[2] = {ws, ws + 2 * tile_bytes};
-  uint16_t *o_part = reinterpret_cast<uint16_t *>(ws + 4 * tile_bytes);
-  float *o_acc = reinterpret_cast<float *>(ws + 5 * tile_bytes);
-  float *l_part = reinterpret_cast<float *>(ws + 5 * tile_bytes + tile_elems * 4);
+  char *k_all = ws, *v_all = ws + (size_t)P * tile_bytes;
+  uint16_t *o_part = reinterpret_cast<uint16_t *>(ws + kv_area);
+  float *o_acc = reinterpret_cast<float *>(ws + kv_area + tile_bytes);
+  float *l_part = reinterpret_cast<float *>(ws + kv_area + tile_bytes + tile_elems * 4);
   float *l_acc[2] = {l_part + (size_t)H * n_local, l_part + 2 * (size_t)H * n_local};
   int l_cur[2] = {0, 0};  // which L accumulator holds the current value, per half
   const int next = (r->rank + 1) % P, prev = (r->rank - 1 + P) % P;
   const int64_t hs = (int64_t)n_local * D;
 
   FA_CUDA_CHECK(cudaEventRecord(r->inputs_ready, st));
-  const void *curK = K, *curV = V;
   // which local rows have received a contribution so far (for the first/last flags per row range)
   bool touched[2] = {false, false};  // [first half, second half] when causal; [all, -] otherwise
-  for (int s = 0; s < P; ++s) {
-    if (s + 1 < P) {
-      // ---- ship the chunk we hold to the next rank while we work on it ----
-      if (s == 0) FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->inputs_ready, 0));
-      // the slot we are about to overwrite was the chunk step s-1 computed on (s >= 2 only)
-      if (s >= 2) FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->compute_done[(s - 1) & 1], 0));
-      char *dst = slot[s & 1];
-      FA_NCCL_CHECK(api->GroupStart());
-      FA_NCCL_CHECK(api->Send(curK, tile_bytes, kNcclUint8, next, r->comm, r->comm_stream));
-      FA_NCCL_CHECK(api->Send(curV, tile_bytes, kNcclUint8, next, r->comm, r->comm_stream));
-      FA_NCCL_CHECK(api->Recv(dst, tile_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-      FA_NCCL_CHECK(api->Recv(dst + tile_bytes, tile_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-      FA_NCCL_CHECK(api->GroupEnd());
-      FA_CUDA_CHECK(cudaEventRecord(r->recv_done[s & 1], r->comm_stream));
-    }
-    // ---- local work on the chunk we hold ----
+  // ---- local work of ring step s on the chunk (curK, curV) of rank (rank - s) mod P ----
+  auto do_step = [&](int s, const void *curK, const void *curV) -> int {
     Block b;
     ring_plan(r->rank, P, s, n_local, is_causal, &b);
     const uint16_t *q = reinterpret_cast<const uint16_t *>(Q) + (int64_t)b.q_off * D;
@@ -367,6 +372,47 @@ int fa_ring_attention_forward(void *ring, const void *Q, const void *K, const vo
       touched[hf] = true;
       l_cur[hf] ^= 1;
     }
+    return FA_OK;
+  };
+
+  if (gather) {
+    // the previous call's readers of the gather area are ordered before this one by the stream: `st`
+    // reached inputs_ready only after them
+    FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->inputs_ready, 0));
+    FA_NCCL_CHECK(api->GroupStart());
+    FA_NCCL_CHECK(api->AllGather(K, k_all, tile_bytes, kNcclUint8, r->comm, r->comm_stream));
+    FA_NCCL_CHECK(api->AllGather(V, v_all, tile_bytes, kNcclUint8, r->comm, r->comm_stream));
+    FA_NCCL_CHECK(api->GroupEnd());
+    FA_CUDA_CHECK(cudaEventRecord(r->recv_done[0], r->comm_stream));
+    int rc = do_step(0, K, V);  // the local block runs under the gather
+    if (rc != FA_OK) return rc;
+    FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->recv_done[0], 0));
+    for (int s = 1; s < P; ++s) {
+      const int src = ((r->rank - s) % P + P) % P;
+      rc = do_step(s, k_all + (size_t)src * tile_bytes, v_all + (size_t)src * tile_bytes);
+      if (rc != FA_OK) return rc;
+    }
+    return FA_OK;
+  }
+
+  const void *curK = K, *curV = V;
+  for (int s = 0; s < P; ++s) {
+    if (s + 1 < P) {
+      // ---- ship the chunk we hold to the next rank while we work on it ----
+      if (s == 0) FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->inputs_ready, 0));
+      // the slot we are about to overwrite was the chunk step s-1 computed on (s >= 2 only)
+      if (s >= 2) FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->compute_done[(s - 1) & 1], 0));
+      char *dst = slot[s & 1];
+      FA_NCCL_CHECK(api->GroupStart());
+      FA_NCCL_CHECK(api->Send(curK, tile_bytes, kNcclUint8, next, r->comm, r->comm_stream));
+      FA_NCCL_CHECK(api->Send(curV, tile_bytes, kNcclUint8, next, r->comm, r->comm_stream));
+      FA_NCCL_CHECK(api->Recv(dst, tile_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+      FA_NCCL_CHECK(api->Recv(dst + tile_bytes, tile_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+      FA_NCCL_CHECK(api->GroupEnd());
+      FA_CUDA_CHECK(cudaEventRecord(r->recv_done[s & 1], r->comm_stream));
+    }
+    int rc = do_step(s, curK, curV);
+    if (rc != FA_OK) return rc;
     FA_CUDA_CHECK(cudaEventRecord(r->compute_done[s & 1], st));
     if (s + 1 < P) {
       FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->recv_done[s & 1], 0));

@@ -138,6 +138,10 @@ int fa_ring_get_unique_id(void *out, int bytes);            /* rank 0; ship the 
 int fa_ring_create(fa_ring_t *ring, const void *unique_id, int rank, int world, int device);
 int fa_ring_destroy(fa_ring_t ring);
 size_t fa_ring_workspace_bytes(int n_local, int D, int H, int dtype);
+/* Optional all-gather forward mode (set FA_RING_GATHER=1 and pass a workspace of at least this size):
+ * every rank's K/V is gathered once under the local block and the remote blocks run back to back --
+ * for medium N on many GPUs, where a ring step computes for less time than its K/V hand-off takes. */
+size_t fa_ring_workspace_bytes_gather(int world, int n_local, int D, int H, int dtype);
 int fa_ring_attention_forward(fa_ring_t ring, const void *Q, const void *K, const void *V, void *O,
                               float *L_out, int n_local, int D, int H, float scale, int is_causal,
                               int dtype, void *workspace, size_t workspace_bytes, fa_stream_t stream);

@@ -18,7 +18,10 @@ ap.add_argument("--causal", type=int, default=1)
 ap.add_argument("--check", type=int, default=1)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--bwd", type=int, default=0)
+ap.add_argument("--gather", type=int, default=0, help="1: all-gather forward mode (sets FA_RING_GATHER=1)")
 a = ap.parse_args()
+if a.gather:
+    os.environ["FA_RING_GATHER"] = "1"  # read by the library at its first ring forward
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -38,7 +41,8 @@ if a.check:
 else:
     Q, K, V = (torch.rand((H, n_local, D), device="cuda", generator=g).mul_(2).sub_(1).to(torch.bfloat16) for _ in range(3))
 O = torch.zeros_like(Q); L = torch.zeros((H, n_local), device="cuda")
-wsb = ring.workspace_bytes(n_local, D, H, fa.BF16); ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+wsb = ring.workspace_bytes_gather(world, n_local, D, H, fa.BF16) if a.gather else ring.workspace_bytes(n_local, D, H, fa.BF16)
+ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
 st = torch.cuda.current_stream()
 run = lambda: ring.forward(Q, K, V, O, L, n_local, D, H, scale, a.causal, fa.BF16, ws, wsb, st)
 run(); torch.cuda.synchronize()
@@ -82,7 +86,7 @@ flops = 4.0 * H * N * N * D * (0.5 if a.causal else 1.0) * (3.5 if a.bwd else 1.
 if rank == 0:
     print(json.dumps({"ring_forward": True, "world": world, "N_total": N, "n_local": n_local, "H": H, "d": D, "causal": a.causal,
                       "ms": ms.item(), "tflops_total": flops / ms.item() / 1e9, "tflops_per_gpu": flops / ms.item() / 1e9 / world,
-                      "max_abs_err_vs_single_gpu": err, "max_abs_L_err": errl, "bwd": a.bwd,
+                      "gather": a.gather, "max_abs_err_vs_single_gpu": err, "max_abs_L_err": errl, "bwd": a.bwd,
                       "bwd_rel_err_dq_dk_dv_vs_single_gpu": berr}), flush=True)
 ring.close()
 dist.destroy_process_group()
