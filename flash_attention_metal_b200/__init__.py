@@ -20,6 +20,8 @@ LIB_PATH = os.environ.get("FA_B200_LIB") or os.path.join(_HERE, "libflash_attn_b
 
 FP16, BF16 = 0, 1
 NAIVE, V1, V2 = 0, 1, 2
+#: ring transports (FA_RING_TRANSPORT_* of the header)
+TRANSPORT_AUTO, TRANSPORT_NCCL, TRANSPORT_NCCL_GATHER, TRANSPORT_PEER = 0, 1, 2, 3
 
 #: every symbol include/flash_attn_b200.h declares (tests check they are all exported)
 EXPORTS = (
@@ -30,6 +32,10 @@ EXPORTS = (
     "flash_attention_v4_half_rect", "fa_ring_unique_id_bytes", "fa_ring_get_unique_id", "fa_ring_create",
     "fa_ring_destroy", "fa_ring_workspace_bytes", "fa_ring_attention_forward", "fa_ring_plan", "fa_ring_local_rows",
     "fa_ring_workspace_bytes_backward", "fa_ring_attention_backward", "fa_ring_workspace_bytes_gather",
+    "fa_ring_create_ex", "fa_ring_transport", "fa_ring_workspace_bytes_ex",
+    "flash_attention_backward_rect", "fa_rowsum_delta",
+    "fa_mgpu_create", "fa_mgpu_destroy", "fa_mgpu_device_count", "fa_mgpu_stream", "fa_mgpu_synchronize",
+    "fa_mgpu_sharded_forward", "fa_mgpu_sharded_backward", "fa_mgpu_ring_forward", "fa_mgpu_ring_backward",
     "fa_last_error", "fa_version", "fa_device_count", "fa_launch_count", "fa_reset_launch_count",
 )
 
@@ -84,6 +90,23 @@ def lib() -> C.CDLL:
         L.fa_ring_workspace_bytes_backward.argtypes = [i32, i32, i32, i32]
         L.fa_ring_workspace_bytes_backward.restype = sz
         L.fa_ring_attention_backward.argtypes = [vp] * 10 + [i32, i32, i32, f32, i32, i32, vp, sz, vp]
+        L.fa_ring_create_ex.argtypes = [C.POINTER(vp), vp, i32, i32, i32, i32]
+        L.fa_ring_transport.argtypes = [vp]
+        L.fa_ring_workspace_bytes_ex.argtypes = [i32, i32, i32, i32, i32, i32]
+        L.fa_ring_workspace_bytes_ex.restype = sz
+        L.flash_attention_backward_rect.argtypes = [vp] * 9 + [i32, i32, i32, f32, i64, i64, i64, i64, i32, i32, i32, i32, vp]
+        L.fa_rowsum_delta.argtypes = [vp, vp, vp, i32, i32, i64, i64, i32, i32, i32, vp]
+        pp = C.POINTER(vp)
+        L.fa_mgpu_create.argtypes = [C.POINTER(vp), C.POINTER(i32), i32]
+        L.fa_mgpu_destroy.argtypes = [vp]
+        L.fa_mgpu_device_count.argtypes = [vp]
+        L.fa_mgpu_stream.argtypes = [vp, i32]
+        L.fa_mgpu_stream.restype = vp
+        L.fa_mgpu_synchronize.argtypes = [vp]
+        L.fa_mgpu_sharded_forward.argtypes = [vp] + [pp] * 5 + [i32, i32, f32, i32, C.POINTER(i32), i32]
+        L.fa_mgpu_sharded_backward.argtypes = [vp] + [pp] * 9 + [i32, i32, f32, i32, C.POINTER(i32), i32]
+        L.fa_mgpu_ring_forward.argtypes = [vp] + [pp] * 5 + [i32, i32, i32, f32, i32, i32]
+        L.fa_mgpu_ring_backward.argtypes = [vp] + [pp] * 9 + [i32, i32, i32, f32, i32, i32]
         ip = C.POINTER(i32)
         L.fa_ring_plan.argtypes = [i32, i32, i32, i32, i32, ip, ip, ip, ip, ip, ip]
         L.fa_ring_local_rows.argtypes = [i32, i32, i32, i32, C.POINTER(i64), ip]
@@ -165,19 +188,18 @@ def ring_unique_id() -> bytes:
 
 
 class Ring:
-    """fa_ring_t wrapper.  `unique_id` comes from ring_unique_id() on rank 0 and must reach every rank."""
+    """fa_ring_t wrapper.  `unique_id` comes from ring_unique_id() on rank 0 and must reach every rank.
+    `transport` (TRANSPORT_*) must be the same on every rank; `self.transport` is the one in effect."""
 
-    def __init__(self, unique_id: bytes, rank: int, world: int, device: int):
+    def __init__(self, unique_id: bytes, rank: int, world: int, device: int, transport: int = TRANSPORT_AUTO):
         self.handle = C.c_void_p()
         self.rank, self.world = rank, world
-        _check(lib().fa_ring_create(C.byref(self.handle), unique_id, rank, world, device))
+        _check(lib().fa_ring_create_ex(C.byref(self.handle), unique_id, rank, world, device, transport))
+        self.transport = int(lib().fa_ring_transport(self.handle))
 
     def workspace_bytes(self, n_local, D, H, dtype) -> int:
-        return int(lib().fa_ring_workspace_bytes(n_local, D, H, dtype))
-
-    def workspace_bytes_gather(self, world, n_local, D, H, dtype):
-        """Workspace of the all-gather forward mode (used when FA_RING_GATHER=1)."""
-        return int(lib().fa_ring_workspace_bytes_gather(world, n_local, D, H, dtype))
+        """Forward workspace for this ring's transport."""
+        return int(lib().fa_ring_workspace_bytes_ex(self.world, self.transport, n_local, D, H, dtype))
 
     def forward(self, Q, K, V, O, L_out, n_local, D, H, scale, is_causal, dtype, workspace, workspace_bytes, stream=None):
         _check(lib().fa_ring_attention_forward(self.handle, _ptr(Q), _ptr(K), _ptr(V), _ptr(O), _ptr(L_out), n_local, D,
@@ -199,6 +221,55 @@ class Ring:
             self.handle = C.c_void_p()
 
 
+def _ptr_array(items):
+    arr = (C.c_void_p * len(items))()
+    for i, x in enumerate(items):
+        arr[i] = _ptr(x)
+    return arr
+
+
+class Mgpu:
+    """fa_mgpu_t wrapper: one process driving several GPUs.  Tensor arguments are lists with one device
+    tensor (or pointer) per group device.  Calls enqueue on the group's streams; synchronize() waits."""
+
+    def __init__(self, devices):
+        self.handle = C.c_void_p()
+        self.devices = list(devices)
+        arr = (C.c_int * len(self.devices))(*self.devices)
+        _check(lib().fa_mgpu_create(C.byref(self.handle), arr, len(self.devices)))
+
+    def stream(self, index) -> int:
+        return lib().fa_mgpu_stream(self.handle, index)
+
+    def synchronize(self):
+        _check(lib().fa_mgpu_synchronize(self.handle))
+
+    def _heads(self, heads):
+        return (C.c_int * len(heads))(*heads)
+
+    def sharded_forward(self, Q, K, V, O, L, N, D, scale, is_causal, heads, dtype):
+        _check(lib().fa_mgpu_sharded_forward(self.handle, _ptr_array(Q), _ptr_array(K), _ptr_array(V), _ptr_array(O),
+                                             None if L is None else _ptr_array(L), N, D, scale, int(is_causal),
+                                             self._heads(heads), dtype))
+
+    def sharded_backward(self, Q, K, V, O, dO, L, dQ, dK, dV, N, D, scale, is_causal, heads, dtype):
+        _check(lib().fa_mgpu_sharded_backward(self.handle, *(_ptr_array(t) for t in (Q, K, V, O, dO, L, dQ, dK, dV)), N, D,
+                                              scale, int(is_causal), self._heads(heads), dtype))
+
+    def ring_forward(self, Q, K, V, O, L, n_local, D, H, scale, is_causal, dtype):
+        _check(lib().fa_mgpu_ring_forward(self.handle, _ptr_array(Q), _ptr_array(K), _ptr_array(V), _ptr_array(O),
+                                          None if L is None else _ptr_array(L), n_local, D, H, scale, int(is_causal), dtype))
+
+    def ring_backward(self, Q, K, V, O, dO, L, dQ, dK, dV, n_local, D, H, scale, is_causal, dtype):
+        _check(lib().fa_mgpu_ring_backward(self.handle, *(_ptr_array(t) for t in (Q, K, V, O, dO, L, dQ, dK, dV)), n_local, D,
+                                           H, scale, int(is_causal), dtype))
+
+    def close(self):
+        if self.handle:
+            lib().fa_mgpu_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+
 def ring_plan(rank, world, step, n_local, is_causal):
     """(src_rank, q_off, q_rows, k_off, k_rows, block_causal) of the block `rank` computes at `step`."""
     out = [C.c_int() for _ in range(6)]
@@ -212,6 +283,19 @@ def ring_local_rows(rank, world, n_local, is_causal):
     rows = (C.c_int * 2)()
     _check(lib().fa_ring_local_rows(rank, world, n_local, int(is_causal), first, rows))
     return [(int(first[i]), int(rows[i])) for i in range(2) if rows[i] > 0]
+
+
+def flash_attention_backward_rect(Q, K, V, dO, L, delta, dQ, dK, dV, Nq, Nk, D, scale, q_batch_stride, q_head_stride,
+                                  kv_batch_stride, kv_head_stride, acc_dq=False, B=1, H=1, dtype=FP16, stream=None):
+    """Cross-attention gradients (Nq != Nk, non-causal); L and delta are those of the FULL softmax rows."""
+    _check(lib().flash_attention_backward_rect(_ptr(Q), _ptr(K), _ptr(V), _ptr(dO), _ptr(L), _ptr(delta), _ptr(dQ), _ptr(dK),
+                                               _ptr(dV), Nq, Nk, D, scale, q_batch_stride, q_head_stride, kv_batch_stride,
+                                               kv_head_stride, int(acc_dq), B, H, dtype, _stream(stream)))
+
+
+def rowsum_delta(O, dO, delta, N, D, batch_stride, head_stride, B=1, H=1, dtype=FP16, stream=None):
+    """delta[b, h, i] = sum_d O * dO (kernels.metal:983-990)."""
+    _check(lib().fa_rowsum_delta(_ptr(O), _ptr(dO), _ptr(delta), N, D, batch_stride, head_stride, B, H, dtype, _stream(stream)))
 
 
 def workspace_bytes_backward(N, D, B, H) -> int:

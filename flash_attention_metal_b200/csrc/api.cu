@@ -24,7 +24,26 @@ void count_launch(int n) { g_launches += n; }
 
 }  // namespace fa
 
-namespace fa { long long *g_fwd_prof = nullptr; }
+#if defined(FA_FWD_TRACE) || defined(FA_BWD_TRACE)
+namespace fa { long long *g_trace_buffer = nullptr; }
+#endif
+
+namespace fa {
+static std::atomic<int> g_l2_group_mb{48};
+int l2_group_mb() { return g_l2_group_mb.load(std::memory_order_relaxed); }
+
+int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cache[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cache[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+}  // namespace fa
 
 using namespace fa;
 
@@ -35,9 +54,30 @@ int fa_version(void) { return 100; }
 long fa_launch_count(void) { return g_launches; }
 void fa_reset_launch_count(void) { g_launches = 0; }
 
-// Development aid (not in the public header): device buffer of >= 32 int64 that the backward dK/dV
-// kernel fills with phase timings of one CTA; pass NULL to switch it off.
-void fa_debug_set_prof_buffer(long long *dev) { g_fwd_prof = dev; }
+#if defined(FA_FWD_TRACE) || defined(FA_BWD_TRACE)
+// Trace builds only (-DFA_FWD_TRACE / -DFA_BWD_TRACE, tests/trace_probe*.py): device buffer the kernels
+// fill with clock64() timestamps of one CTA; NULL switches it off.  Not compiled into the product.
+void fa_debug_set_prof_buffer(long long *dev) { g_trace_buffer = dev; }
+#endif
+
+// Development aid (not in the public header): one ring-attention partial on one GPU -- the forward over
+// a chunk of keys whose epilogue folds the result into the running fp32 (O_acc, L_acc) pair (FwdMerge:
+// lo / hi = 0 none, 1 first, 2 middle, 3 last, for rows below / from half_rows).  Tests chain it over
+// key chunks to check the fused merge without a second GPU.
+int fa_debug_forward_partial(const void *Q, const void *K, const void *V, void *O, float *L, float *O_acc, float *L_acc,
+                             int Nq, int Nk, int D, float scale, int H, int is_causal, int lo, int hi, int half_rows,
+                             int dtype, fa_stream_t stream) {
+  FwdMerge m{O_acc, L_acc, lo, hi, half_rows};
+  return launch_fwd_tc_rect(Q, K, V, O, L, Nq, Nk, D, scale, (int64_t)H * Nq * D, (int64_t)Nq * D, (int64_t)H * Nk * D,
+                            (int64_t)Nk * D, is_causal, 1, H, dtype, (cudaStream_t)stream, &m);
+}
+
+// Development aid (not in the public header): L2 budget of a dispatch group of heads, in MB.
+void fa_debug_set_l2_group_mb(int mb) { g_l2_group_mb.store(mb < 0 ? 0 : mb, std::memory_order_relaxed); }
+
+// Development aid (not in the public header): cap of the key-split cluster size of small forward
+// launches (default 4; tests exercise 8).
+void fa_debug_set_fwd_split_max(int cap) { set_fwd_split_max(cap); }
 
 // Development aid (not in the public header): the dispatch geometry sched.cuh picks for a launch
 // of `n_blocks` blocks per head -- out = {heads per group, grid.x, grid.y, grid.z}.  Host logic only.
@@ -106,6 +146,26 @@ int flash_attention_backward(const void *Q, const void *K, const void *V, const 
                              void *workspace, size_t workspace_bytes, fa_stream_t stream) {
   return launch_bwd_tc(Q, K, V, O, dO, L, dQ, dK, dV, N, D, scale, batch_stride, head_stride,
                        is_causal, B, H, dtype, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int flash_attention_backward_rect(const void *Q, const void *K, const void *V, const void *dO, const float *L,
+                                  const float *delta, float *dQ, float *dK, float *dV, int Nq, int Nk, int D,
+                                  float scale, int64_t q_batch_stride, int64_t q_head_stride,
+                                  int64_t kv_batch_stride, int64_t kv_head_stride, int acc_dq, int B, int H,
+                                  int dtype, fa_stream_t stream) {
+  FA_REQUIRE(dQ != nullptr || dK != nullptr, "nothing to compute: dQ, dK and dV are all null");
+  return launch_bwd_tc_rect(Q, K, V, dO, L, delta, dQ, dK, dV, Nq, Nk, D, scale, q_batch_stride, q_head_stride,
+                            kv_batch_stride, kv_head_stride, 0, acc_dq, B, H, dtype, (cudaStream_t)stream);
+}
+
+int fa_rowsum_delta(const void *O, const void *dO, float *delta, int N, int D, int64_t batch_stride,
+                    int64_t head_stride, int B, int H, int dtype, fa_stream_t stream) {
+  FA_REQUIRE(O && dO && delta && N >= 1 && B >= 1 && H >= 1, "bad arguments");
+  FA_REQUIRE(D == 64 || D == 128, "D must be 64 or 128 (got %d)", D);
+  FA_REQUIRE(dtype == FA_DTYPE_FP16 || dtype == FA_DTYPE_BF16, "dtype must be FA_DTYPE_FP16 or FA_DTYPE_BF16");
+  FA_REQUIRE(aligned16(O) && aligned16(dO), "O and dO must be 16-byte aligned");
+  FA_REQUIRE(batch_stride % D == 0 && head_stride % D == 0, "strides must be multiples of D");
+  return launch_bwd_delta(O, dO, delta, N, D, batch_stride, head_stride, B, H, dtype, (cudaStream_t)stream);
 }
 
 size_t fa_workspace_bytes_backward(int N, int D, int B, int H) {

@@ -93,7 +93,9 @@ struct BwdParams {
   int causal;         // requires Nq == Nk
   int acc_dq;         // dQ += instead of dQ = (ring attention accumulates over K/V chunks)
   int group, n_heads; // dispatch order (sched.cuh)
-  long long *prof;  // optional phase-timing buffer (development aid), normally null
+#ifdef FA_BWD_TRACE
+  long long *prof;  // phase-timing buffer (trace builds only)
+#endif
 };
 
 // ---------------------------------------------------------------------------
@@ -260,21 +262,28 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     };
     float stat_next = fetch_stat(0);
     const uint64_t scale_log2_2 = pack_f32x2(p.scale_log2, p.scale_log2), scale_2 = pack_f32x2(p.scale, p.scale);
+#ifdef FA_BWD_TRACE
     const bool prof = p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0;
     long long tw_x = 0, t_p1 = 0, tw_y = 0, t_p2 = 0, t_top = 0, t_top2 = 0, t_begin = prof ? clock64() : 0;
+#define FA_PCLK(var) long long var = prof ? clock64() : 0
+#define FA_PDO(stmt) do { if (prof) { stmt; } } while (0)
+#else
+#define FA_PCLK(var) do {} while (0)
+#define FA_PDO(stmt) do {} while (0)
+#endif
     for (int i = 0; i < n; ++i) {
       const int q0 = (i_start + i) * 128 + wg * 64;  // first query column of this warpgroup's half
       float *ld = sLD + (wg * 2 + (i & 1)) * 128;
-      long long ca = prof ? clock64() : 0;
+      FA_PCLK(ca);
       ld[tid] = stat_next * stat_coef;
-      long long cb = prof ? clock64() : 0;
+      FA_PCLK(cb);
       stat_next = fetch_stat(i + 1);
       named_bar_sync(1 + wg, 128);
-      if (prof) { t_top += cb - ca; t_top2 += clock64() - cb; }
+      FA_PDO(t_top += cb - ca; t_top2 += clock64() - cb);
       // ---- phase 1: P^T = exp2(S^T * c - L * log2e) ----
-      long long c0 = prof ? clock64() : 0;
+      FA_PCLK(c0);
       mbar_wait(x_full, i & 1);
-      long long c1 = prof ? clock64() : 0;
+      FA_PCLK(c1);
       tc_fence_after();
       uint32_t pr[2][32];  // S^T, then P^T (fp32 bits), kept for phase 2
       tmem_ld32(tX, pr[0]);
@@ -322,9 +331,9 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
       // ---- phase 2: dS^T = P^T o (dP^T * scale - D * scale) ----
-      long long c2 = prof ? clock64() : 0;
+      FA_PCLK(c2);
       mbar_wait(y_full, i & 1);
-      long long c3 = prof ? clock64() : 0;
+      FA_PCLK(c3);
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -349,12 +358,16 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_arrive_warp(&ds_ready[kDkdvParts == 2 ? c : 0]);
         }
       }
-      if (prof) { tw_x += c1 - c0; t_p1 += c2 - c1; tw_y += c3 - c2; t_p2 += clock64() - c3; }
+      FA_PDO(tw_x += c1 - c0; t_p1 += c2 - c1; tw_y += c3 - c2; t_p2 += clock64() - c3);
     }
+#ifdef FA_BWD_TRACE
     if (prof) {
       long long *o = p.prof + wg * 8;
       o[0] = n; o[1] = tw_x; o[2] = t_p1; o[3] = tw_y; o[4] = t_p2; o[5] = clock64() - t_begin; o[6] = t_top; o[7] = t_top2;
     }
+#endif
+#undef FA_PCLK
+#undef FA_PDO
     // ------------------------------ epilogue ------------------------------
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -419,14 +432,21 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mma_ss(tY, kmajor_desc(sV_a, kk), kmajor_desc(do_addr(i), kk), idesc_xy, kk > 0);
           tc_commit(y_full);
         };
+#ifdef FA_BWD_TRACE
         const bool mprof = p.prof != nullptr && blockIdx.x == gridDim.x / 2 && blockIdx.y == 0 && blockIdx.z == 0;
-        long long mw_p = 0, mw_ds = 0, m_begin = mprof ? clock64() : 0;
+        long long mw_p = 0, mw_ds = 0, m_begin = mprof ? clock64() : 0, w0 = 0;
+#define FA_MCLK() do { if (mprof) w0 = clock64(); } while (0)
+#define FA_MACC(acc) do { if (mprof) acc += clock64() - w0; } while (0)
+#else
+#define FA_MCLK() do {} while (0)
+#define FA_MACC(acc) do {} while (0)
+#endif
         mbar_wait(res_full, 0);
         tc_fence_after();
         issue_x(0);
         issue_y(0);
         for (int i = 0; i < n; ++i) {
-          long long w0 = mprof ? clock64() : 0;
+          FA_MCLK();
           // dV += P^T dO_i (K = 128 query rows); part c = columns [32c, 32c+32) of both warpgroups'
           // halves = k-steps {2c, 2c+1, 4+2c, 5+2c}
 #pragma unroll
@@ -440,10 +460,10 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                      (i > 0 || part > 0 || q > 0) ? 1u : 0u);
             }
           }
-          if (mprof) mw_p += clock64() - w0;
+          FA_MACC(mw_p);
           tc_commit(&do_empty[i % Cfg::kDoSlots]);
           if (i + 1 < n) issue_x(i + 1);
-          w0 = mprof ? clock64() : 0;
+          FA_MCLK();
 #pragma unroll
           for (int part = 0; part < kDkdvParts; ++part) {  // dK += dS^T Q_i
             mbar_wait(&ds_ready[part], i & 1);
@@ -455,12 +475,16 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                      (i > 0 || part > 0 || q > 0) ? 1u : 0u);
             }
           }
-          if (mprof) mw_ds += clock64() - w0;
+          FA_MACC(mw_ds);
           tc_commit(&q_empty[i % Cfg::kQSlots]);
           if (i == n - 1) tc_commit(acc_full);
           if (i + 1 < n) issue_y(i + 1);
         }
+#ifdef FA_BWD_TRACE
         if (mprof) { p.prof[16] = mw_p; p.prof[17] = mw_ds; p.prof[18] = clock64() - m_begin; }
+#endif
+#undef FA_MCLK
+#undef FA_MACC
       }
       __syncwarp();
     }
@@ -750,14 +774,16 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 }
 
 template <int D, int IS_BF16>
-int launch_bwd_impl(const CUtensorMap *maps, const BwdParams &p, int B, cudaStream_t stream) {
+int launch_bwd_impl(const CUtensorMap *const *maps, const BwdParams &p, int B, cudaStream_t stream) {
   static DeviceOnce configured;  // the attribute is per device
-  if (configured.first_use()) {
+  const int rc = configured.run([] {
     FA_CUDA_CHECK(cudaFuncSetAttribute(bwd_dkdv_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        DkdvCfg<D>::kSmemBytes));
     FA_CUDA_CHECK(cudaFuncSetAttribute(bwd_dq_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        DqCfg<D>::kSmemBytes));
-  }
+    return (int)FA_OK;
+  });
+  if (rc != FA_OK) return rc;
   // maps: [0] Q, [1] K, [2] V, [3] dO, all with 128-row boxes
   BwdParams q = p;
   q.n_heads = B * p.H;
@@ -765,13 +791,13 @@ int launch_bwd_impl(const CUtensorMap *maps, const BwdParams &p, int B, cudaStre
   if ((p.Nk + 127) / 128 > 65535 || (p.Nq + 255) / 256 > 65535) q.group = 1;  // grid.y limit of the grouped form
   if (p.dK != nullptr) {
     bwd_dkdv_kernel<D, IS_BF16><<<dispatch_grid(q.group, (p.Nk + 127) / 128, p.H, B), kBwdThreads, DkdvCfg<D>::kSmemBytes, stream>>>(
-        maps[0], maps[1], maps[2], maps[3], q);
+        *maps[0], *maps[1], *maps[2], *maps[3], q);
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();
   }
   if (p.dQ != nullptr) {
     bwd_dq_kernel<D, IS_BF16><<<dispatch_grid(q.group, (p.Nq + 255) / 256, p.H, B), kBwdThreads, DqCfg<D>::kSmemBytes, stream>>>(
-        maps[0], maps[1], maps[2], maps[3], q);
+        *maps[0], *maps[1], *maps[2], *maps[3], q);
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();
   }
@@ -820,13 +846,13 @@ int launch_bwd_tc_rect(const void *Q, const void *K, const void *V, const void *
   FA_REQUIRE((H == 1 || (q_head_stride >= (int64_t)Nq * D && kv_head_stride >= (int64_t)Nk * D)) &&
                  (B == 1 || (q_batch_stride >= (int64_t)Nq * D && kv_batch_stride >= (int64_t)Nk * D)),
              "heads overlap: stride smaller than N*D");
-  CUtensorMap maps[4];
+  const CUtensorMap *maps[4];
   int rc;
-  if ((rc = make_tensor_map_bhnd(&maps[0], Q, dtype, Nq, D, H, B, q_head_stride, q_batch_stride, 128)) != FA_OK) return rc;
-  if ((rc = make_tensor_map_bhnd(&maps[1], K, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, 128)) != FA_OK) return rc;
-  if ((rc = make_tensor_map_bhnd(&maps[2], V, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, 128)) != FA_OK) return rc;
-  if ((rc = make_tensor_map_bhnd(&maps[3], dO, dtype, Nq, D, H, B, q_head_stride, q_batch_stride, 128)) != FA_OK) return rc;
-  BwdParams p;
+  if ((rc = tensor_map_bhnd(&maps[0], Q, dtype, Nq, D, H, B, q_head_stride, q_batch_stride, 128)) != FA_OK) return rc;
+  if ((rc = tensor_map_bhnd(&maps[1], K, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, 128)) != FA_OK) return rc;
+  if ((rc = tensor_map_bhnd(&maps[2], V, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, 128)) != FA_OK) return rc;
+  if ((rc = tensor_map_bhnd(&maps[3], dO, dtype, Nq, D, H, B, q_head_stride, q_batch_stride, 128)) != FA_OK) return rc;
+  BwdParams p = {};
   p.L = L;
   p.delta = delta;
   p.dQ = dQ; p.dK = dK; p.dV = dV;
@@ -839,7 +865,9 @@ int launch_bwd_tc_rect(const void *Q, const void *K, const void *V, const void *
   p.kv_head_stride = kv_head_stride;
   p.causal = is_causal ? 1 : 0;
   p.acc_dq = acc_dq ? 1 : 0;
-  p.prof = g_fwd_prof;
+#ifdef FA_BWD_TRACE
+  p.prof = g_trace_buffer;
+#endif
   if (D == 64)
     return dtype == FA_DTYPE_BF16 ? launch_bwd_impl<64, 1>(maps, p, B, stream) : launch_bwd_impl<64, 0>(maps, p, B, stream);
   return dtype == FA_DTYPE_BF16 ? launch_bwd_impl<128, 1>(maps, p, B, stream) : launch_bwd_impl<128, 0>(maps, p, B, stream);

@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "flash_attn_b200.h"
 
 namespace fa {
@@ -24,17 +27,32 @@ void count_launch(int n = 1);
     if (!(cond)) return ::fa::set_error(FA_ERR_INVALID, __VA_ARGS__);                  \
   } while (0)
 
-// "once per CUDA device" flag for per-device function attributes (max dynamic shared memory)
+// "once per CUDA device" guard for per-device function attributes (max dynamic shared memory).
+// Thread-safe (one host thread per GPU is a supported calling pattern); a device is marked done only
+// after its set-up succeeded, so a transient failure is retried by the next call.
 struct DeviceOnce {
-  bool done[64] = {};
-  bool first_use() {
+  std::atomic<bool> done[64];
+  std::mutex mu;
+  DeviceOnce() { for (auto &d : done) d.store(false, std::memory_order_relaxed); }
+  template <typename F>
+  int run(F &&setup) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-    if (done[dev]) return false;
-    done[dev] = true;
-    return true;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return setup();
+    if (done[dev].load(std::memory_order_acquire)) return FA_OK;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done[dev].load(std::memory_order_relaxed)) return FA_OK;
+    const int rc = setup();
+    if (rc == FA_OK) done[dev].store(true, std::memory_order_release);
+    return rc;
   }
 };
+
+// L2 budget (MB) of one dispatch group of heads (sched.cuh).  48 is the measured optimum on B200's
+// 126 MB L2; only tests change it (fa_debug_set_l2_group_mb) to prove results do not depend on it.
+int l2_group_mb();
+
+// SM count of the current device (cached per device, thread-safe; 148 if the query fails)
+int device_sm_count();
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
@@ -48,13 +66,26 @@ int launch_fwd_tc(const void *Q, const void *K, const void *V, void *O, float *L
                   float scale, int64_t batch_stride, int64_t head_stride, int is_causal, int B, int H,
                   int dtype, cudaStream_t stream);
 
+// Ring attention: fold this launch's partial result into a running fp32 (O_acc, L_acc) pair in the
+// kernel epilogue (modes per row range: rows < half_rows use `lo`, the rest `hi`).
+//   0 none: plain launch      1 first: acc = partial      2 middle: acc = acc (+) partial
+//   3 last : O, L = acc (+) partial (16-bit O, final L)
+struct FwdMerge {
+  float *O_acc;   // fp32, addressed like O (same strides)
+  float *L_acc;   // fp32, addressed like L
+  int lo, hi, half_rows;
+};
+
 // rectangular (Nq x Nk, separate Q/O and K/V strides) form used by ring attention
 int launch_fwd_tc_rect(const void *Q, const void *K, const void *V, void *O, float *L, int Nq, int Nk,
                        int D, float scale, int64_t q_batch_stride, int64_t q_head_stride,
                        int64_t kv_batch_stride, int64_t kv_head_stride, int is_causal, int B, int H,
-                       int dtype, cudaStream_t stream);
+                       int dtype, cudaStream_t stream, const FwdMerge *merge = nullptr);
+void set_fwd_split_max(int cap);  // development aid behind fa_debug_set_fwd_split_max
 
-extern long long *g_fwd_prof;  // development aid: phase-timing buffer, see fa_debug_set_prof_buffer
+#if defined(FA_FWD_TRACE) || defined(FA_BWD_TRACE)
+extern long long *g_trace_buffer;  // trace builds only (never in the product build): see fa_debug_set_prof_buffer
+#endif
 
 // backward (bwd_tc.cu)
 int launch_bwd_tc(const void *Q, const void *K, const void *V, const void *O, const void *dO,

@@ -359,10 +359,12 @@ int launch_fp32_d(int variant, const float *Q, const float *K, const float *V, f
   } else {
     const int smem = (int)sizeof(V2Smem<D>);
     static DeviceOnce configured;  // the attribute is per device
-    if (configured.first_use()) {
+    const int rc = configured.run([smem] {
       FA_CUDA_CHECK(cudaFuncSetAttribute(flash_attention_v2_kernel<D>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    }
+      return (int)FA_OK;
+    });
+    if (rc != FA_OK) return rc;
     dim3 grid((N + V2_BM - 1) / V2_BM, H, B);
     flash_attention_v2_kernel<D><<<grid, V2_THREADS, smem, st>>>(Q, K, V, O, N, scale, causal, bs, hs);
   }

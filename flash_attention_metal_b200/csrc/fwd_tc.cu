@@ -35,6 +35,9 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
+#include <algorithm>
+#include <atomic>
+
 #include "fa_internal.h"
 #include "sched.cuh"
 #include "sm100_ptx.cuh"
@@ -100,7 +103,9 @@ struct FwdCfg {
 #endif
 
 struct FwdParams {
-  long long *prof;
+#ifdef FA_FWD_TRACE
+  long long *prof;  // hand-off timestamps (trace builds only)
+#endif
   void *O;
   float *L;
   int Nq;             // query rows (= rows of O and L)
@@ -112,7 +117,16 @@ struct FwdParams {
   int causal;         // requires Nq == Nk
   int group, n_blocks, n_heads;  // dispatch order (sched.cuh)
   int split;          // CTAs per cluster that share one row block, each taking 1/split of the keys
+  // Ring attention: the launch is one (Q block x K/V chunk) partial of a longer softmax row.  The
+  // epilogue folds it into a running fp32 (O_acc, L_acc) pair with the online-softmax rule
+  // (kernels.metal:784-791) instead of a separate merge kernel; rows below `half_rows` (the first
+  // zig-zag chunk) and the rest can be at different points of their sequence of partials.
+  float *O_acc;       // fp32, addressed like O
+  float *L_acc;       // fp32, addressed like L
+  int merge_lo, merge_hi, half_rows;  // kMerge* per row range
 };
+
+enum { kMergeNone = 0, kMergeFirst = 1, kMergeMiddle = 2, kMergeLast = 3 };
 
 template <int D, int IS_BF16>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -320,31 +334,68 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #ifdef FA_FWD_TRACE
     if (p.prof != nullptr && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.prof[262] = clock64();
 #endif
+    // Normalise the accumulator in TMEM and store it.  kMergeNone / kMergeLast write the 16-bit O and L;
+    // kMergeFirst / kMergeMiddle write the running fp32 pair; Middle / Last first fold the running pair in.
+    auto store_rows = [&](float m_fin, float l_fin) {
+      const int mode = grow < p.half_rows ? p.merge_lo : p.merge_hi;
+      const int64_t head_off = (int64_t)b * p.batch_stride + (int64_t)h * p.head_stride;
+      const int64_t li = head_off / D + grow;
+      const bool in_range = grow < p.Nq;
+      float lse = m_fin * p.scale + lg2(l_fin) * kLn2;
+      float w_part = 1.f / l_fin, w_acc = 0.f;
+      if (mode >= kMergeMiddle && in_range) {
+        const float la = p.L_acc[li];
+        const float mx = fmaxf(la, lse);
+        const float ea = ex2((la - mx) * kLog2e), ep = ex2((lse - mx) * kLog2e);
+        const float l_new = mx + lg2(ea + ep) * kLn2;
+        w_acc = ex2((la - l_new) * kLog2e);
+        w_part *= ex2((lse - l_new) * kLog2e);
+        lse = l_new;
+      }
+      const bool to_acc = mode == kMergeFirst || mode == kMergeMiddle;
+      uint16_t *orow = reinterpret_cast<uint16_t *>(p.O) + head_off + (int64_t)grow * D;
+      float *arow = p.O_acc + head_off + (int64_t)grow * D;
+#pragma unroll
+      for (int c = 0; c < D / 32; ++c) {
+        uint32_t o[32];
+        tmem_ld32(tO + c * 32, o);
+        tmem_wait_ld();
+        if (!in_range) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(o[i]) * w_part;
+        if (mode >= kMergeMiddle) {
+          const float4 *a4 = reinterpret_cast<const float4 *>(arow + c * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 a = a4[i];
+            v[4 * i] = fmaf(a.x, w_acc, v[4 * i]); v[4 * i + 1] = fmaf(a.y, w_acc, v[4 * i + 1]);
+            v[4 * i + 2] = fmaf(a.z, w_acc, v[4 * i + 2]); v[4 * i + 3] = fmaf(a.w, w_acc, v[4 * i + 3]);
+          }
+        }
+        if (to_acc) {
+          float4 *d4 = reinterpret_cast<float4 *>(arow + c * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            dst[i] = make_uint4(pack2<IS_BF16>(v[8 * i], v[8 * i + 1]), pack2<IS_BF16>(v[8 * i + 2], v[8 * i + 3]),
+                                pack2<IS_BF16>(v[8 * i + 4], v[8 * i + 5]), pack2<IS_BF16>(v[8 * i + 6], v[8 * i + 7]));
+        }
+      }
+      if (in_range) {
+        if (to_acc) p.L_acc[li] = lse;
+        else if (p.L != nullptr) p.L[li] = lse;
+      }
+    };
     if (split == 1) {
       if (nt > 0) {
         // ------------------------------ epilogue -------------------------------
         mbar_wait(&o_full[t], 0);
         tc_fence_after();
-        const float inv_l = 1.f / l_run;
-        const int64_t head_off = (int64_t)b * p.batch_stride + (int64_t)h * p.head_stride;
-        uint16_t *orow = reinterpret_cast<uint16_t *>(p.O) + head_off + (int64_t)grow * D;
-  #pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tO + c * 32, o);
-          tmem_wait_ld();
-          uint32_t w[16];
-  #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            w[i] = pack2<IS_BF16>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
-          if (grow < p.Nq) {
-            uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
-  #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-          }
-        }
-        if (p.L != nullptr && grow < p.Nq)
-          p.L[head_off / D + grow] = m_run * p.scale + lg2(l_run) * kLn2;
+        store_rows(m_run, l_run);
       }
     } else {
       // ------------------------- epilogue of a key split ----------------------
@@ -414,27 +465,7 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
           o_valid = true;
         }
       }
-      if (crank == 0 && n_t[t] > 0) {
-        const float inv_l = 1.f / l_cur;
-        const int64_t head_off = (int64_t)b * p.batch_stride + (int64_t)h * p.head_stride;
-        uint16_t *orow = reinterpret_cast<uint16_t *>(p.O) + head_off + (int64_t)grow * D;
-#pragma unroll
-        for (int c = 0; c < D / 32; ++c) {
-          uint32_t o[32];
-          tmem_ld32(tO + c * 32, o);
-          tmem_wait_ld();
-          uint32_t w[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            w[i] = pack2<IS_BF16>(__uint_as_float(o[2 * i]) * inv_l, __uint_as_float(o[2 * i + 1]) * inv_l);
-          if (grow < p.Nq) {
-            uint4 *dst = reinterpret_cast<uint4 *>(orow + c * 32);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-          }
-        }
-        if (p.L != nullptr && grow < p.Nq) p.L[head_off / D + grow] = m_cur * p.scale + lg2(l_cur) * kLn2;
-      }
+      if (crank == 0 && n_t[t] > 0) store_rows(m_cur, l_cur);
     }
   } else {
     setmaxnreg_dec<64>();
@@ -571,72 +602,82 @@ fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 #endif
 }
 
+// largest cluster of these one-CTA-per-SM blocks the current device can co-schedule (asked once per device)
+template <int D, int IS_BF16>
+int max_cluster_size() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+  int best = cache[dev].load(std::memory_order_relaxed);
+  if (best != 0) return best;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = FwdCfg<D>::kSmemBytes;
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  best = 1;
+  for (int c = 8; c > 1; c /= 2) {
+    int n_clusters = 0;
+    cfg.gridDim = dim3((unsigned)c, 1, 1);
+    attr[0].val.clusterDim.x = (unsigned)c;
+    if (cudaOccupancyMaxActiveClusters(&n_clusters, fwd_tc_kernel<D, IS_BF16>, &cfg) == cudaSuccess && n_clusters > 0) {
+      best = c;
+      break;
+    }
+    (void)cudaGetLastError();
+  }
+  cache[dev].store(best, std::memory_order_relaxed);
+  return best;
+}
+
+// Upper bound on the key-split cluster size.  4 by default: clusters of 8 work but measured slower
+// (single head N=4096: 56 us unsplit, 37 / 28 / 42 us at 2 / 4 / 8: a third merge round, and eight
+// whole-SM CTAs have to be co-scheduled in one GPC).  fa_debug_set_fwd_split_max changes it (tests).
+std::atomic<int> g_split_cap{4};
+
 template <int D, int IS_BF16>
 int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUtensorMap &tmV,
                        const FwdParams &p, int B, cudaStream_t stream) {
   using Cfg = FwdCfg<D>;
   static DeviceOnce configured;  // the attribute is per device
-  if (configured.first_use()) {
-    FA_CUDA_CHECK(cudaFuncSetAttribute(fwd_tc_kernel<D, IS_BF16>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-  }
+  int rc = configured.run([] {
+    FA_CUDA_CHECK(cudaFuncSetAttribute(fwd_tc_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::kSmemBytes));
+    return (int)FA_OK;
+  });
+  if (rc != FA_OK) return rc;
   FwdParams q = p;
   q.n_blocks = (p.Nq + 2 * kBM - 1) / (2 * kBM);
   q.n_heads = B * p.H;
   q.group = dispatch_group(p.causal != 0, (int64_t)2 * p.Nk * D * 2, q.n_heads);
   if (q.n_blocks > 65535) q.group = 1;  // grid.y limit of the grouped form
-  // fewer row blocks than half the SMs: several CTAs (one cluster) per row block, splitting the keys
-  int n_sm = 148;
-  {
-    static int sm_count[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
-      if (sm_count[dev] == 0) cudaDeviceGetAttribute(&sm_count[dev], cudaDevAttrMultiProcessorCount, dev);
-      if (sm_count[dev] > 0) n_sm = sm_count[dev];
-    }
-  }
+  // fewer row blocks than half the SMs: several CTAs (one cluster) per row block, splitting the keys:
   // largest power of two that still fits one wave and leaves every rank at least four key tiles of
-  // the longest row.  Clusters of 8 work (FA_FWD_SPLIT_MAX=8) but measured slower than 4 (single
-  // head N=4096: 56 us unsplit, 37 / 28 / 42 us at 2 / 4 / 8: a third merge round, and eight
-  // whole-SM CTAs have to be co-scheduled in one GPC).
+  // the longest row.  A ring-attention partial (merge mode set) is never split: its epilogue already
+  // merges with the running result.
+  const int n_sm = device_sm_count();
   q.split = 1;
-  static const int split_cap = [] { const char *e = getenv("FA_FWD_SPLIT_MAX"); return e ? atoi(e) : 4; }();
+  const int split_cap = (p.merge_lo | p.merge_hi) ? 1 : g_split_cap.load(std::memory_order_relaxed);
   while (q.split < split_cap && 2 * q.split * q.n_blocks * q.n_heads <= n_sm && (p.Nk + kBN - 1) / kBN >= 4 * q.split) q.split *= 2;
-  cudaLaunchConfig_t cfg = {};
-  cudaLaunchAttribute attr[1];
+  if (q.split > 1) q.split = std::min(q.split, max_cluster_size<D, IS_BF16>());
   if (q.split > 1) {
-    // largest cluster of these one-CTA-per-SM blocks the device can co-schedule (asked once per device)
-    static int max_cluster[64] = {};
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
     attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)q.split;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (max_cluster[dev] == 0) {
-      int best = 1;
-      for (int c = 8; c > 1; c /= 2) {
-        int n_clusters = 0;
-        cfg.gridDim = dim3((unsigned)c, 1, 1);
-        attr[0].val.clusterDim.x = (unsigned)c;
-        if (cudaOccupancyMaxActiveClusters(&n_clusters, fwd_tc_kernel<D, IS_BF16>, &cfg) == cudaSuccess && n_clusters > 0) {
-          best = c;
-          break;
-        }
-        (void)cudaGetLastError();
-      }
-      max_cluster[dev] = best;
-    }
-    if (q.split > max_cluster[dev]) q.split = max_cluster[dev];
-  }
-  if (q.split > 1) {
     q.group = 1;
     cfg.gridDim = dim3((unsigned)(q.n_blocks * q.split), (unsigned)p.H, (unsigned)B);
-    attr[0].val.clusterDim.x = (unsigned)q.split;
     FA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, fwd_tc_kernel<D, IS_BF16>, tmQ, tmK, tmV, q));
   } else {
     fwd_tc_kernel<D, IS_BF16><<<dispatch_grid(q.group, q.n_blocks, p.H, B), kThreads, Cfg::kSmemBytes, stream>>>(tmQ, tmK, tmV, q);
@@ -648,10 +689,12 @@ int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUt
 
 }  // namespace
 
+void set_fwd_split_max(int cap) { g_split_cap.store(cap < 1 ? 1 : (cap > 8 ? 8 : cap), std::memory_order_relaxed); }
+
 int launch_fwd_tc_rect(const void *Q, const void *K, const void *V, void *O, float *L, int Nq, int Nk,
                        int D, float scale, int64_t q_batch_stride, int64_t q_head_stride,
                        int64_t kv_batch_stride, int64_t kv_head_stride, int is_causal, int B, int H,
-                       int dtype, cudaStream_t stream) {
+                       int dtype, cudaStream_t stream, const FwdMerge *merge) {
   FA_REQUIRE(Q && K && V && O, "null tensor pointer");
   FA_REQUIRE(Nq >= 1 && Nk >= 1, "N must be >= 1 (got %d x %d)", Nq, Nk);
   FA_REQUIRE(!is_causal || Nq == Nk, "causal attention needs Nq == Nk");
@@ -667,13 +710,15 @@ int launch_fwd_tc_rect(const void *Q, const void *K, const void *V, void *O, flo
              "heads overlap: stride smaller than N*D");
   FA_REQUIRE(L == nullptr || (q_head_stride % D == 0 && q_batch_stride % D == 0),
              "L_out needs strides that are multiples of D (L index = offset / D, kernels.metal:623)");
-  CUtensorMap tmQ, tmK, tmV;
+  const CUtensorMap *tmQ, *tmK, *tmV;
   int rc;
-  if ((rc = make_tensor_map_bhnd(&tmQ, Q, dtype, Nq, D, H, B, q_head_stride, q_batch_stride, kBM)) != FA_OK) return rc;
-  if ((rc = make_tensor_map_bhnd(&tmK, K, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, kBN)) != FA_OK) return rc;
-  if ((rc = make_tensor_map_bhnd(&tmV, V, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, kBN)) != FA_OK) return rc;
-  FwdParams p;
-  p.prof = g_fwd_prof;
+  if ((rc = tensor_map_bhnd(&tmQ, Q, dtype, Nq, D, H, B, q_head_stride, q_batch_stride, kBM)) != FA_OK) return rc;
+  if ((rc = tensor_map_bhnd(&tmK, K, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, kBN)) != FA_OK) return rc;
+  if ((rc = tensor_map_bhnd(&tmV, V, dtype, Nk, D, H, B, kv_head_stride, kv_batch_stride, kBN)) != FA_OK) return rc;
+  FwdParams p = {};
+#ifdef FA_FWD_TRACE
+  p.prof = g_trace_buffer;
+#endif
   p.O = O;
   p.L = L;
   p.Nq = Nq;
@@ -684,18 +729,27 @@ int launch_fwd_tc_rect(const void *Q, const void *K, const void *V, void *O, flo
   p.batch_stride = q_batch_stride;
   p.head_stride = q_head_stride;
   p.causal = is_causal ? 1 : 0;
+  if (merge != nullptr && (merge->lo != kMergeNone || merge->hi != kMergeNone)) {
+    FA_REQUIRE(merge->O_acc && merge->L_acc && aligned16(merge->O_acc), "merge needs 16-byte aligned O_acc and L_acc");
+    FA_REQUIRE(q_head_stride % D == 0 && q_batch_stride % D == 0, "merge needs strides that are multiples of D");
+    p.O_acc = merge->O_acc;
+    p.L_acc = merge->L_acc;
+    p.merge_lo = merge->lo;
+    p.merge_hi = merge->hi;
+    p.half_rows = merge->half_rows;
+  }
   if (D == 64)
-    return dtype == FA_DTYPE_BF16 ? launch_fwd_tc_impl<64, 1>(tmQ, tmK, tmV, p, B, stream)
-                                  : launch_fwd_tc_impl<64, 0>(tmQ, tmK, tmV, p, B, stream);
-  return dtype == FA_DTYPE_BF16 ? launch_fwd_tc_impl<128, 1>(tmQ, tmK, tmV, p, B, stream)
-                                : launch_fwd_tc_impl<128, 0>(tmQ, tmK, tmV, p, B, stream);
+    return dtype == FA_DTYPE_BF16 ? launch_fwd_tc_impl<64, 1>(*tmQ, *tmK, *tmV, p, B, stream)
+                                  : launch_fwd_tc_impl<64, 0>(*tmQ, *tmK, *tmV, p, B, stream);
+  return dtype == FA_DTYPE_BF16 ? launch_fwd_tc_impl<128, 1>(*tmQ, *tmK, *tmV, p, B, stream)
+                                : launch_fwd_tc_impl<128, 0>(*tmQ, *tmK, *tmV, p, B, stream);
 }
 
 int launch_fwd_tc(const void *Q, const void *K, const void *V, void *O, float *L, int N, int D,
                   float scale, int64_t batch_stride, int64_t head_stride, int is_causal, int B, int H,
                   int dtype, cudaStream_t stream) {
   return launch_fwd_tc_rect(Q, K, V, O, L, N, N, D, scale, batch_stride, head_stride, batch_stride, head_stride,
-                            is_causal, B, H, dtype, stream);
+                            is_causal, B, H, dtype, stream, nullptr);
 }
 
 }  // namespace fa

@@ -1,0 +1,235 @@
+// fa_mgpu_*: one process driving several GPUs of one box (last table row; the
+// reference's harness is a single process, main.mm:881-1204).  The group owns one stream per device,
+// grow-only scratch, and -- for ring attention -- one Ring per device wired to its peers with plain
+// peer access (no NCCL, no IPC: one address space).  Every call only ENQUEUES work on the group's
+// streams, device after device, from the calling thread; fa_mgpu_synchronize waits for all of it.
+//
+//   * B x H sharding (BASELINE config 4): heads never interact (kernels.metal:622), so device i runs
+//     its own heads with the ordinary kernels and nothing is exchanged.
+//   * ring / context-parallel attention (config 5): the same driver as fa_ring_attention_* with the
+//     PEER transport -- copy-engine pulls over NVLink, flags driven by stream memory operations.
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "fa_internal.h"
+#include "ring.h"
+
+namespace fa {
+
+struct MgpuGroup {
+  int n = 0;
+  int devices[kRingMaxWorld] = {};
+  Ring *rings[kRingMaxWorld] = {};
+  cudaStream_t streams[kRingMaxWorld] = {};
+  void *ws[kRingMaxWorld] = {};      // per-device scratch (ring workspace / backward delta)
+  size_t ws_cap[kRingMaxWorld] = {};
+};
+
+// Grow every rank's peer-visible window (called from the first rank's ring call that needs more).
+int mgpu_grow_windows(MgpuGroup *g, size_t bytes) {
+  const size_t cap = (bytes + (size_t(1) << 21) - 1) & ~((size_t(1) << 21) - 1);
+  for (int i = 0; i < g->n; ++i) {  // nothing may still be reading the old windows
+    FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
+    FA_CUDA_CHECK(cudaDeviceSynchronize());
+  }
+  for (int i = 0; i < g->n; ++i) {
+    Ring *r = g->rings[i];
+    FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
+    if (r->data) cudaFree(r->data);
+    r->data = nullptr;
+    r->data_cap = 0;
+    void *p = nullptr;
+    FA_CUDA_CHECK(cudaMalloc(&p, cap));
+    r->data = reinterpret_cast<char *>(p);
+    r->data_cap = cap;
+  }
+  for (int i = 0; i < g->n; ++i)
+    for (int j = 0; j < g->n; ++j) g->rings[i]->peer_data[j] = g->rings[j]->data;
+  return FA_OK;
+}
+
+namespace {
+
+int group_scratch(MgpuGroup *g, int i, size_t bytes, void **out) {
+  if (g->ws_cap[i] < bytes) {
+    FA_CUDA_CHECK(cudaStreamSynchronize(g->streams[i]));
+    if (g->ws[i]) cudaFree(g->ws[i]);
+    g->ws[i] = nullptr;
+    g->ws_cap[i] = 0;
+    FA_CUDA_CHECK(cudaMalloc(&g->ws[i], bytes));
+    g->ws_cap[i] = bytes;
+  }
+  *out = g->ws[i];
+  return FA_OK;
+}
+
+void group_free(MgpuGroup *g) {
+  if (!g) return;
+  for (int i = 0; i < g->n; ++i) {
+    cudaSetDevice(g->devices[i]);
+    cudaDeviceSynchronize();
+  }
+  for (int i = 0; i < g->n; ++i) {
+    cudaSetDevice(g->devices[i]);
+    if (g->rings[i]) {
+      g->rings[i]->group = nullptr;  // ring_free then frees the windows like a stand-alone ring's
+      for (int p = 0; p < kRingMaxWorld; ++p) { g->rings[i]->peer_data[p] = nullptr; g->rings[i]->peer_flags[p] = nullptr; }
+      ring_free(g->rings[i]);
+    }
+    if (g->ws[i]) cudaFree(g->ws[i]);
+    if (g->streams[i]) cudaStreamDestroy(g->streams[i]);
+  }
+  (void)cudaGetLastError();
+  delete g;
+}
+
+}  // namespace
+}  // namespace fa
+
+using namespace fa;
+
+extern "C" {
+
+int fa_mgpu_create(void **out, const int *devices, int n_devices) {
+  FA_REQUIRE(out && devices && n_devices >= 1 && n_devices <= kRingMaxWorld, "bad device list (1..%d devices)", kRingMaxWorld);
+  int visible = 0;
+  FA_CUDA_CHECK(cudaGetDeviceCount(&visible));
+  for (int i = 0; i < n_devices; ++i) {
+    FA_REQUIRE(devices[i] >= 0 && devices[i] < visible, "device %d is not visible (%d devices)", devices[i], visible);
+    for (int j = 0; j < i; ++j) FA_REQUIRE(devices[i] != devices[j], "device %d is listed twice", devices[i]);
+  }
+  MgpuGroup *g = new MgpuGroup();
+  g->n = n_devices;
+  auto fail = [&](int rc) { group_free(g); return rc; };
+  for (int i = 0; i < n_devices; ++i) {
+    g->devices[i] = devices[i];
+    if (cudaSetDevice(devices[i]) != cudaSuccess) return fail(set_error(FA_ERR_CUDA, "cudaSetDevice(%d) failed", devices[i]));
+    for (int j = 0; j < n_devices; ++j) {
+      if (j == i) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+      if (!can) return fail(set_error(FA_ERR_UNSUPPORTED, "device %d cannot access device %d as a peer", devices[i], devices[j]));
+      const cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+        return fail(set_error(FA_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", devices[i], devices[j], cudaGetErrorString(e)));
+      (void)cudaGetLastError();
+    }
+    if (cudaStreamCreateWithFlags(&g->streams[i], cudaStreamNonBlocking) != cudaSuccess)
+      return fail(set_error(FA_ERR_CUDA, "cudaStreamCreate failed on device %d", devices[i]));
+    Ring *r = new Ring();
+    g->rings[i] = r;
+    r->group = g;
+    r->rank = i; r->world = n_devices; r->device = devices[i];
+    r->transport = FA_RING_TRANSPORT_PEER;
+    int rc = ring_init_streams(r);
+    if (rc == FA_OK) rc = ring_alloc_flags(r);
+    if (rc != FA_OK) return fail(rc);
+  }
+  for (int i = 0; i < n_devices; ++i)
+    for (int j = 0; j < n_devices; ++j) g->rings[i]->peer_flags[j] = g->rings[j]->flags;
+  *out = g;
+  return FA_OK;
+}
+
+int fa_mgpu_destroy(void *group) {
+  group_free(reinterpret_cast<MgpuGroup *>(group));
+  return FA_OK;
+}
+
+int fa_mgpu_device_count(void *group) {
+  MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
+  return g ? g->n : 0;
+}
+
+fa_stream_t fa_mgpu_stream(void *group, int index) {
+  MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
+  return (g && index >= 0 && index < g->n) ? (fa_stream_t)g->streams[index] : nullptr;
+}
+
+int fa_mgpu_synchronize(void *group) {
+  MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
+  FA_REQUIRE(g, "null group");
+  for (int i = 0; i < g->n; ++i) {
+    FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
+    FA_CUDA_CHECK(cudaStreamSynchronize(g->streams[i]));
+  }
+  return FA_OK;
+}
+
+int fa_mgpu_sharded_forward(void *group, const void *const *Q, const void *const *K, const void *const *V,
+                            void *const *O, float *const *L, int N, int D, float scale, int is_causal,
+                            const int *heads, int dtype) {
+  MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
+  FA_REQUIRE(g && Q && K && V && O && heads, "null argument");
+  for (int i = 0; i < g->n; ++i) {
+    if (heads[i] <= 0) continue;
+    FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
+    const int64_t hs = (int64_t)N * D;
+    const int rc = launch_fwd_tc(Q[i], K[i], V[i], O[i], L ? L[i] : nullptr, N, D, scale, hs * heads[i], hs, is_causal, 1,
+                                 heads[i], dtype, g->streams[i]);
+    if (rc != FA_OK) return rc;
+  }
+  return FA_OK;
+}
+
+int fa_mgpu_sharded_backward(void *group, const void *const *Q, const void *const *K, const void *const *V,
+                             const void *const *O, const void *const *dO, const float *const *L, float *const *dQ,
+                             float *const *dK, float *const *dV, int N, int D, float scale, int is_causal,
+                             const int *heads, int dtype) {
+  MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
+  FA_REQUIRE(g && Q && K && V && O && dO && L && dQ && dK && dV && heads, "null argument");
+  for (int i = 0; i < g->n; ++i) {
+    if (heads[i] <= 0) continue;
+    FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
+    const int64_t hs = (int64_t)N * D;
+    const size_t wsb = fa_workspace_bytes_backward(N, D, 1, heads[i]);
+    void *ws = nullptr;
+    int rc = group_scratch(g, i, wsb, &ws);
+    if (rc != FA_OK) return rc;
+    rc = launch_bwd_tc(Q[i], K[i], V[i], O[i], dO[i], L[i], dQ[i], dK[i], dV[i], N, D, scale, hs * heads[i], hs, is_causal, 1,
+                       heads[i], dtype, ws, wsb, g->streams[i]);
+    if (rc != FA_OK) return rc;
+  }
+  return FA_OK;
+}
+
+int fa_mgpu_ring_forward(void *group, const void *const *Q, const void *const *K, const void *const *V, void *const *O,
+                         float *const *L, int n_local, int D, int H, float scale, int is_causal, int dtype) {
+  MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
+  FA_REQUIRE(g && Q && K && V && O, "null argument");
+  const size_t wsb = fa_ring_workspace_bytes_ex(g->n, FA_RING_TRANSPORT_PEER, n_local, D, H, dtype);
+  FA_REQUIRE(wsb > 0, "bad shape");
+  for (int i = 0; i < g->n; ++i) {
+    FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
+    void *ws = nullptr;
+    int rc = group_scratch(g, i, wsb, &ws);
+    if (rc != FA_OK) return rc;
+    rc = fa_ring_attention_forward(g->rings[i], Q[i], K[i], V[i], O[i], L ? L[i] : nullptr, n_local, D, H, scale, is_causal,
+                                   dtype, ws, wsb, g->streams[i]);
+    if (rc != FA_OK) return rc;
+  }
+  return FA_OK;
+}
+
+int fa_mgpu_ring_backward(void *group, const void *const *Q, const void *const *K, const void *const *V,
+                          const void *const *O, const void *const *dO, const float *const *L, float *const *dQ,
+                          float *const *dK, float *const *dV, int n_local, int D, int H, float scale, int is_causal,
+                          int dtype) {
+  MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
+  FA_REQUIRE(g && Q && K && V && O && dO && L && dQ && dK && dV, "null argument");
+  const size_t wsb = fa_ring_workspace_bytes_backward(n_local, D, H, dtype);
+  FA_REQUIRE(wsb > 0, "bad shape");
+  for (int i = 0; i < g->n; ++i) {
+    FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
+    void *ws = nullptr;
+    int rc = group_scratch(g, i, wsb, &ws);
+    if (rc != FA_OK) return rc;
+    rc = fa_ring_attention_backward(g->rings[i], Q[i], K[i], V[i], O[i], dO[i], L[i], dQ[i], dK[i], dV[i], n_local, D, H, scale,
+                                    is_causal, dtype, ws, wsb, g->streams[i]);
+    if (rc != FA_OK) return rc;
+  }
+  return FA_OK;
+}
+
+}  // extern "C"

@@ -1,10 +1,10 @@
-// Ring / context-parallel attention forward across the GPUs of one box (not in the
-// reference: BASELINE.json config 5).  One process per GPU; each rank owns n_local query
-// rows of every head and the matching K/V rows.  The K/V chunk travels around the ring with
-// NCCL point-to-point calls (ncclSend/ncclRecv over NVLink) on a side stream, double
-// buffered, one step ahead of the tile loop that consumes it; partial (O, L) results are
-// merged with the online-softmax rule the reference uses inside its kernel
-// (kernels.metal:784-791):  L' = log(e^L1 + e^L2),  O' = O1 e^(L1-L') + O2 e^(L2-L').
+// Ring / context-parallel attention across the GPUs of one box (not in the reference:
+// BASELINE.json config 5).  Each rank owns n_local query rows of every head and the matching
+// K/V rows; at step s it attends its queries to the K/V chunk of rank (rank - s) mod P and folds
+// the partial result into a running fp32 (O, L) pair with the online-softmax rule the reference
+// uses inside its kernel (kernels.metal:784-791):  L' = log(e^L1 + e^L2),
+// O' = O1 e^(L1-L') + O2 e^(L2-L').  The fold happens in the EPILOGUE of the forward kernel
+// (FwdMerge, fwd_tc.cu): one launch per ring step, no separate merge kernel, no 16-bit round trip.
 //
 // Causal balance: zig-zag.  The sequence is cut into 2P chunks of c = n_local/2 rows and
 // rank r holds chunks r and 2P-1-r (local rows [0,c) and [c,2c)).  Then at every ring step
@@ -12,30 +12,46 @@
 //   step 0 (own K/V)      : causal attention over the local 2c rows in local order
 //   K/V from a lower rank : all 2c local queries x the first c received keys
 //   K/V from a higher rank: the last c local queries x all 2c received keys
-// and fully masked chunk pairs are never computed or waited for.
+// and fully masked chunk pairs are never computed, waited for, or (peer transport) transferred.
 //
-// NCCL is dlopen()ed so that the library has no link-time dependency on it.
+// Transports (chosen once per ring, agreed by all ranks at creation -- never per call, never by
+// environment variable):
+//   PEER        every rank exposes a window of device memory to its peers (CUDA IPC between
+//               processes, plain peer access inside one process).  K/V chunks are PULLED straight
+//               from their owner by the copy engines (cudaMemcpyAsync over NVLink; through
+//               NVSwitch every owner is one hop away, so nothing is forwarded hop by hop), and
+//               ranks synchronise with 32-bit flags in each other's windows driven by stream
+//               memory operations (cuStreamWriteValue32 / cuStreamWaitValue32).  No SM is used for
+//               communication: the 1-CTA-per-SM compute grids keep the whole GPU.
+//   NCCL        ncclSend/ncclRecv ring on a side stream (NCCL's copy kernels compete with the
+//               compute grid for SMs: measured 67 GB/s effective at medium N in round 1).
+//   NCCL_GATHER one ncclAllGather of all K/V under the local block, remote blocks back to back.
+// NCCL is dlopen()ed so that the library has no link-time dependency on it; a single-process
+// group (fa_mgpu_*, mgpu.cu) uses the PEER transport without NCCL at all.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <math_constants.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "fa_internal.h"
+#include "ring.h"
 
 namespace fa {
 namespace {
 
 // ---- the handful of NCCL entry points used, resolved at run time ------------------
-struct NcclUniqueId { char internal[128]; };
-typedef void *NcclComm;
 struct NcclApi {
   int (*GetUniqueId)(NcclUniqueId *);
   int (*CommInitRank)(NcclComm *, int, NcclUniqueId, int);
   int (*CommDestroy)(NcclComm);
   int (*Send)(const void *, size_t, int /*dtype*/, int, NcclComm, cudaStream_t);
   int (*Recv)(void *, size_t, int, int, NcclComm, cudaStream_t);
-  int (*AllGather)(const void *, void *, size_t, int /*dtype*/, NcclComm, cudaStream_t);  // optional
+  int (*AllGather)(const void *, void *, size_t, int /*dtype*/, NcclComm, cudaStream_t);
   int (*GroupStart)();
   int (*GroupEnd)();
   const char *(*GetErrorString)(int);
@@ -45,50 +61,125 @@ constexpr int kNcclUint8 = 1;
 
 NcclApi *nccl() {
   static NcclApi api;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     const char *names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char *n : names) {
       api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
       if (api.handle) break;
     }
-    if (api.handle) {
+    if (!api.handle) return;
 #define FA_SYM(field, sym) *(void **)(&api.field) = dlsym(api.handle, sym)
-      FA_SYM(GetUniqueId, "ncclGetUniqueId");
-      FA_SYM(CommInitRank, "ncclCommInitRank");
-      FA_SYM(CommDestroy, "ncclCommDestroy");
-      FA_SYM(Send, "ncclSend");
-      FA_SYM(Recv, "ncclRecv");
-      FA_SYM(AllGather, "ncclAllGather");
-      FA_SYM(GroupStart, "ncclGroupStart");
-      FA_SYM(GroupEnd, "ncclGroupEnd");
-      FA_SYM(GetErrorString, "ncclGetErrorString");
+    FA_SYM(GetUniqueId, "ncclGetUniqueId");
+    FA_SYM(CommInitRank, "ncclCommInitRank");
+    FA_SYM(CommDestroy, "ncclCommDestroy");
+    FA_SYM(Send, "ncclSend");
+    FA_SYM(Recv, "ncclRecv");
+    FA_SYM(AllGather, "ncclAllGather");
+    FA_SYM(GroupStart, "ncclGroupStart");
+    FA_SYM(GroupEnd, "ncclGroupEnd");
+    FA_SYM(GetErrorString, "ncclGetErrorString");
 #undef FA_SYM
-      if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.GroupStart || !api.GroupEnd) {
-        dlclose(api.handle);
-        api.handle = nullptr;
-      }
+    if (!api.GetUniqueId || !api.CommInitRank || !api.Send || !api.Recv || !api.AllGather || !api.GroupStart ||
+        !api.GroupEnd) {
+      dlclose(api.handle);
+      api.handle = nullptr;
     }
-  }
+  });
   return api.handle ? &api : nullptr;
 }
 
-#define FA_NCCL_CHECK(expr)                                                                      \
-  do {                                                                                           \
-    int _r = (expr);                                                                             \
-    if (_r != 0)                                                                                 \
-      return set_error(FA_ERR_NCCL, "%s failed: %s", #expr,                                      \
-                       nccl()->GetErrorString ? nccl()->GetErrorString(_r) : "nccl error");      \
+int nccl_error(const char *what, int code) {
+  NcclApi *api = nccl();
+  return set_error(FA_ERR_NCCL, "%s failed: %s", what,
+                   api && api->GetErrorString ? api->GetErrorString(code) : "nccl error");
+}
+#define FA_NCCL_CHECK(expr)                      \
+  do {                                           \
+    int _r = (expr);                             \
+    if (_r != 0) return nccl_error(#expr, _r);   \
   } while (0)
 
-struct Ring {
-  NcclComm comm = nullptr;
-  int rank = 0, world = 1, device = 0;
-  cudaStream_t comm_stream = nullptr;
-  cudaEvent_t inputs_ready = nullptr, recv_done[2] = {nullptr, nullptr}, compute_done[2] = {nullptr, nullptr};
-  cudaEvent_t add_done[2] = {nullptr, nullptr}, acc_recv_done[2] = {nullptr, nullptr};  // backward dK/dV ring
+// A send/recv group that is always closed, also on the error path (an open group would swallow the
+// next NCCL call of this thread).
+template <typename F>
+int nccl_group(NcclApi *api, F &&body) {
+  int rc = api->GroupStart();
+  if (rc != 0) return nccl_error("ncclGroupStart", rc);
+  const int body_rc = body();
+  rc = api->GroupEnd();
+  if (body_rc != FA_OK) return body_rc;
+  if (rc != 0) return nccl_error("ncclGroupEnd", rc);
+  return FA_OK;
+}
+
+// flag words of a rank's flag window
+constexpr int kFlagKvReady = 0;                 // [src]   src's K/V window holds the data of epoch e
+constexpr int kFlagKvDone = kRingMaxWorld;      // [peer]  peer has finished reading my K/V window of epoch e
+constexpr int kFlagAccReady = 2 * kRingMaxWorld;      // prev has published its k-th dK/dV accumulator
+constexpr int kFlagAccDone = 2 * kRingMaxWorld + 1;   // next has pulled my k-th accumulator
+constexpr int kFlagScratch = 256, kFlagScratchWords = 512;  // local staging of flag values (third write mechanism)
+constexpr size_t kFlagBytes = 4096;
+
+// ---- stream memory operations (driver API, resolved through the runtime) ----------
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+typedef CUresult (*MemsetD32AsyncFn)(CUdeviceptr, unsigned int, size_t, CUstream);
+struct MemOps {
+  StreamValue32Fn wait = nullptr, write = nullptr;
+  MemsetD32AsyncFn memset32 = nullptr;
 };
+const MemOps *memops() {
+  static MemOps ops;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    auto get = [](const char *name) -> void * {
+      void *p = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        (void)cudaGetLastError();
+        return nullptr;
+      }
+      return p;
+    };
+    ops.wait = reinterpret_cast<StreamValue32Fn>(get("cuStreamWaitValue32"));
+    ops.write = reinterpret_cast<StreamValue32Fn>(get("cuStreamWriteValue32"));
+    ops.memset32 = reinterpret_cast<MemsetD32AsyncFn>(get("cuMemsetD32Async"));
+  });
+  return &ops;
+}
+
+// stream `st` proceeds once *flag >= value (flag is in this device's memory; peers write it)
+int flag_wait(cudaStream_t st, const uint32_t *flag, uint32_t value) {
+  const MemOps *m = memops();
+  if (!m->wait) return set_error(FA_ERR_UNSUPPORTED, "cuStreamWaitValue32 is not available from the driver");
+  const CUresult r = m->wait((CUstream)st, (CUdeviceptr)(uintptr_t)flag, value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) return set_error(FA_ERR_CUDA, "cuStreamWaitValue32 failed (CUresult %d)", (int)r);
+  return FA_OK;
+}
+// *flag = value, in stream order after everything enqueued on `st` so far.  The flag usually lives in
+// a peer's window.  Three mechanisms, tried in this order and remembered per process: a stream write
+// straight to the peer address; a 32-bit memset of the peer address; a stream write into local
+// scratch followed by a 4-byte copy to the peer (always possible: it is an ordinary peer copy).
+std::atomic<int> g_write_mech{0};
+int flag_write(cudaStream_t st, uint32_t *flag, uint32_t value, Ring *r) {
+  const MemOps *m = memops();
+  int mech = g_write_mech.load(std::memory_order_relaxed);
+  if (mech == 0) {
+    if (m->write && m->write((CUstream)st, (CUdeviceptr)(uintptr_t)flag, value, 0) == CUDA_SUCCESS) return FA_OK;
+    g_write_mech.store(mech = 1, std::memory_order_relaxed);
+  }
+  if (mech == 1) {
+    if (m->memset32 && m->memset32((CUdeviceptr)(uintptr_t)flag, value, 1, (CUstream)st) == CUDA_SUCCESS) return FA_OK;
+    g_write_mech.store(mech = 2, std::memory_order_relaxed);
+  }
+  (void)cudaGetLastError();
+  if (!m->write || !r || !r->flags) return set_error(FA_ERR_UNSUPPORTED, "no way to write a peer flag from a stream");
+  uint32_t *scratch = r->flags + kFlagScratch + (r->scratch_next++ % kFlagScratchWords);
+  const CUresult e = m->write((CUstream)st, (CUdeviceptr)(uintptr_t)scratch, value, 0);
+  if (e != CUDA_SUCCESS) return set_error(FA_ERR_CUDA, "cuStreamWriteValue32 failed (CUresult %d)", (int)e);
+  FA_CUDA_CHECK(cudaMemcpyAsync(flag, scratch, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+  return FA_OK;
+}
 
 // Backward dK/dV ring step: out = (has_in ? in : 0) (+ tmp on the key rows this step touched).
 // One launch covers dK and dV ([2][H, n_local, D] fp32 each, stacked).  Single owner per element.
@@ -107,71 +198,6 @@ __global__ void __launch_bounds__(256) ring_dkv_add_kernel(float *__restrict__ o
   *reinterpret_cast<float4 *>(out + e) = a;
 }
 
-// ---- merge kernel: acc <- acc (+) part, optionally writing the final 16-bit O and L ----
-// One thread per 8 output elements of a row; O_acc fp32 [H, n_local, D], part 16-bit.
-template <int IS_BF16>
-__global__ void __launch_bounds__(256) ring_merge_kernel(
-    float *__restrict__ o_acc, const float *__restrict__ l_acc_in, float *__restrict__ l_acc_out,
-    const uint16_t *__restrict__ o_part,
-    const float *__restrict__ l_part, uint16_t *__restrict__ o_out, float *__restrict__ l_out,
-    int n_local, int D, int row_off, int rows, int first, int last) {
-  const int vec_per_row = D / 8;
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t per_head = (int64_t)rows * vec_per_row;
-  const int h = blockIdx.y;
-  if (idx >= per_head) return;
-  const int r = row_off + (int)(idx / vec_per_row);
-  const int v = (int)(idx % vec_per_row);
-  const int64_t row_idx = (int64_t)h * n_local + r;
-  const int64_t e = row_idx * D + v * 8;
-  const float lp = l_part[row_idx];
-  float w_acc = 0.f, w_part = 1.f, l_new = lp;
-  if (!first) {
-    const float la = l_acc_in[row_idx];
-    const float mx = fmaxf(la, lp);
-    const float ea = __expf(la - mx), ep = __expf(lp - mx);
-    l_new = mx + __logf(ea + ep);
-    w_acc = __expf(la - l_new);
-    w_part = __expf(lp - l_new);
-  }
-  const uint4 pv = *reinterpret_cast<const uint4 *>(o_part + e);
-  const uint32_t pw[4] = {pv.x, pv.y, pv.z, pv.w};
-  float out[8];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float p0, p1;
-    if (IS_BF16) {
-      p0 = __uint_as_float(pw[i] << 16);
-      p1 = __uint_as_float(pw[i] & 0xffff0000u);
-    } else {
-      asm("{.reg .b16 lo, hi; mov.b32 {lo, hi}, %2; cvt.f32.f16 %0, lo; cvt.f32.f16 %1, hi;}"
-          : "=f"(p0), "=f"(p1) : "r"(pw[i]));
-    }
-    out[2 * i] = p0 * w_part;
-    out[2 * i + 1] = p1 * w_part;
-  }
-  if (!first) {
-    const float4 a0 = *reinterpret_cast<const float4 *>(o_acc + e);
-    const float4 a1 = *reinterpret_cast<const float4 *>(o_acc + e + 4);
-    out[0] += a0.x * w_acc; out[1] += a0.y * w_acc; out[2] += a0.z * w_acc; out[3] += a0.w * w_acc;
-    out[4] += a1.x * w_acc; out[5] += a1.y * w_acc; out[6] += a1.z * w_acc; out[7] += a1.w * w_acc;
-  }
-  if (!last) {
-    *reinterpret_cast<float4 *>(o_acc + e) = make_float4(out[0], out[1], out[2], out[3]);
-    *reinterpret_cast<float4 *>(o_acc + e + 4) = make_float4(out[4], out[5], out[6], out[7]);
-    if (v == 0) l_acc_out[row_idx] = l_new;  // other threads of this row still read l_acc_in
-  } else {
-    uint32_t w[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      if (IS_BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(out[2 * i + 1]), "f"(out[2 * i]));
-      else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(out[2 * i + 1]), "f"(out[2 * i]));
-    }
-    *reinterpret_cast<uint4 *>(o_out + e) = make_uint4(w[0], w[1], w[2], w[3]);
-    if (v == 0 && l_out) l_out[row_idx] = l_new;
-  }
-}
-
 struct Block { int src, q_off, q_rows, k_off, k_rows, causal; };
 
 // The schedule (pure host logic, also exported as fa_ring_plan and tested on CPU).
@@ -188,6 +214,194 @@ int ring_plan(int rank, int world, int step, int n_local, int is_causal, Block *
   else if (b->src < rank) *b = Block{b->src, 0, n_local, 0, c, 0};      // every local query sees chunk src only
   else *b = Block{b->src, c, c, 0, n_local, 0};                         // only chunk 2P-1-rank sees both received chunks
   return 0;
+}
+
+int merge_mode(bool first, bool last) {
+  return first ? (last ? 0 : 1) : (last ? 3 : 2);  // kMergeNone / First / Last / Middle (fwd_tc.cu)
+}
+
+
+struct IpcBlob {  // what ranks exchange about a window (padded to 128 bytes)
+  cudaIpcMemHandle_t handle;
+  int ok;
+  char pad[128 - sizeof(cudaIpcMemHandle_t) - sizeof(int)];
+};
+static_assert(sizeof(IpcBlob) == 128, "IpcBlob must be 128 bytes");
+
+// all-gather of one 128-byte blob per rank through NCCL (host in, host out; synchronous)
+int exchange_blobs(Ring *r, const IpcBlob &mine, IpcBlob *all) {
+  NcclApi *api = nccl();
+  if (!api || !r->comm) return set_error(FA_ERR_NCCL, "no NCCL communicator for the handle exchange");
+  FA_CUDA_CHECK(cudaMemcpy(r->xchg + (size_t)r->rank * sizeof(IpcBlob), &mine, sizeof(IpcBlob), cudaMemcpyHostToDevice));
+  FA_NCCL_CHECK(api->AllGather(r->xchg + (size_t)r->rank * sizeof(IpcBlob), r->xchg, sizeof(IpcBlob), kNcclUint8, r->comm,
+                               r->comm_stream));
+  FA_CUDA_CHECK(cudaStreamSynchronize(r->comm_stream));
+  FA_CUDA_CHECK(cudaMemcpy(all, r->xchg, (size_t)r->world * sizeof(IpcBlob), cudaMemcpyDeviceToHost));
+  return FA_OK;
+}
+
+// Map every peer's window `mine` belongs to.  Collective.  *all_ok tells whether every rank succeeded
+// (the same answer on every rank); on failure nothing stays mapped.
+int map_peer_windows(Ring *r, void *mine, void **peer_out, bool *all_ok) {
+  IpcBlob blob = {}, all[kRingMaxWorld];
+  blob.ok = mine != nullptr && cudaIpcGetMemHandle(&blob.handle, mine) == cudaSuccess;
+  (void)cudaGetLastError();
+  int rc = exchange_blobs(r, blob, all);
+  if (rc != FA_OK) return rc;
+  bool ok = true;
+  for (int p = 0; p < r->world; ++p) ok = ok && all[p].ok;
+  for (int p = 0; p < r->world; ++p) peer_out[p] = nullptr;
+  if (ok) {
+    for (int p = 0; p < r->world && ok; ++p) {
+      if (p == r->rank) { peer_out[p] = mine; continue; }
+      if (cudaIpcOpenMemHandle(&peer_out[p], all[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        (void)cudaGetLastError();
+        peer_out[p] = nullptr;
+        ok = false;
+      }
+    }
+  }
+  // second round: did everybody manage to open everything?
+  blob.ok = ok;
+  rc = exchange_blobs(r, blob, all);
+  if (rc != FA_OK) return rc;
+  bool everyone = true;
+  for (int p = 0; p < r->world; ++p) everyone = everyone && all[p].ok;
+  if (!everyone)
+    for (int p = 0; p < r->world; ++p) {
+      if (p != r->rank && peer_out[p]) cudaIpcCloseMemHandle(peer_out[p]);
+      peer_out[p] = nullptr;
+    }
+  *all_ok = everyone;
+  return FA_OK;
+}
+
+void unmap_peer_windows(Ring *r, void **peers) {
+  for (int p = 0; p < r->world; ++p) {
+    if (p != r->rank && peers[p] && !r->group) cudaIpcCloseMemHandle(peers[p]);
+    peers[p] = nullptr;
+  }
+}
+
+}  // namespace
+
+// ---- ring life cycle (also used by mgpu.cu) ----------------------------------------
+int ring_init_streams(Ring *r) {
+  FA_CUDA_CHECK(cudaStreamCreateWithFlags(&r->comm_stream, cudaStreamNonBlocking));
+  FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->inputs_ready, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) {
+    FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->recv_done[i], cudaEventDisableTiming));
+    FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->compute_done[i], cudaEventDisableTiming));
+    FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->add_done[i], cudaEventDisableTiming));
+    FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->acc_recv_done[i], cudaEventDisableTiming));
+  }
+  FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->comm_idle, cudaEventDisableTiming));
+  return FA_OK;
+}
+
+int ring_alloc_flags(Ring *r) {
+  FA_CUDA_CHECK(cudaMalloc(&r->flags, kFlagBytes));
+  FA_CUDA_CHECK(cudaMemset(r->flags, 0, kFlagBytes));
+  return FA_OK;
+}
+
+// Make the peer-visible data window at least `bytes` large.  Collective (every rank calls it with the
+// same size, so every rank takes the same branch); synchronises the device when it has to grow.
+int ring_ensure_window(Ring *r, size_t bytes) {
+  if (r->data_cap >= bytes) return FA_OK;
+  if (r->group) return mgpu_grow_windows(r->group, bytes);  // one process: the group reallocates every rank's window
+  FA_CUDA_CHECK(cudaDeviceSynchronize());
+  unmap_peer_windows(r, reinterpret_cast<void **>(r->peer_data));
+  // nobody may free a window a peer still has mapped: a round of the exchange is the barrier
+  IpcBlob blob = {}, all[kRingMaxWorld];
+  int rc = exchange_blobs(r, blob, all);
+  if (rc != FA_OK) return rc;
+  if (r->data) cudaFree(r->data);
+  r->data = nullptr;
+  r->data_cap = 0;
+  const size_t cap = (bytes + (size_t(1) << 21) - 1) & ~((size_t(1) << 21) - 1);
+  void *p = nullptr;
+  const bool alloc_ok = cudaMalloc(&p, cap) == cudaSuccess;
+  (void)cudaGetLastError();
+  bool ok = false;
+  rc = map_peer_windows(r, alloc_ok ? p : nullptr, reinterpret_cast<void **>(r->peer_data), &ok);
+  if (rc != FA_OK || !ok) {
+    if (p) cudaFree(p);
+    return rc != FA_OK ? rc : set_error(FA_ERR_CUDA, "could not allocate and share a %zu-byte peer window on every rank", cap);
+  }
+  r->data = reinterpret_cast<char *>(p);
+  r->data_cap = cap;
+  return FA_OK;
+}
+
+void ring_free(Ring *r) {
+  if (!r) return;
+  cudaSetDevice(r->device);
+  cudaDeviceSynchronize();
+  if (!r->group) {
+    unmap_peer_windows(r, reinterpret_cast<void **>(r->peer_data));
+    unmap_peer_windows(r, reinterpret_cast<void **>(r->peer_flags));
+  }
+  if (r->comm && nccl() && nccl()->CommDestroy) nccl()->CommDestroy(r->comm);
+  if (r->data) cudaFree(r->data);
+  if (r->flags) cudaFree(r->flags);
+  if (r->xchg) cudaFree(r->xchg);
+  if (r->comm_stream) cudaStreamDestroy(r->comm_stream);
+  if (r->inputs_ready) cudaEventDestroy(r->inputs_ready);
+  if (r->comm_idle) cudaEventDestroy(r->comm_idle);
+  for (int i = 0; i < 2; ++i) {
+    if (r->recv_done[i]) cudaEventDestroy(r->recv_done[i]);
+    if (r->compute_done[i]) cudaEventDestroy(r->compute_done[i]);
+    if (r->add_done[i]) cudaEventDestroy(r->add_done[i]);
+    if (r->acc_recv_done[i]) cudaEventDestroy(r->acc_recv_done[i]);
+  }
+  (void)cudaGetLastError();
+  delete r;
+}
+
+namespace {
+
+// K/V chunk rows [k_off, k_off + k_rows) of every head: contiguous when the whole chunk is wanted,
+// otherwise a strided 2-D copy (both run on the copy engines)
+int copy_rows(void *dst, const void *src, int n_local, int D, int H, int k_off, int k_rows, cudaStream_t st) {
+  const size_t row = (size_t)D * 2;
+  if (k_off == 0 && k_rows == n_local) {
+    FA_CUDA_CHECK(cudaMemcpyAsync(dst, src, (size_t)H * n_local * row, cudaMemcpyDeviceToDevice, st));
+  } else {
+    FA_CUDA_CHECK(cudaMemcpy2DAsync(reinterpret_cast<char *>(dst) + k_off * row, (size_t)n_local * row,
+                                    reinterpret_cast<const char *>(src) + k_off * row, (size_t)n_local * row,
+                                    (size_t)k_rows * row, H, cudaMemcpyDeviceToDevice, st));
+  }
+  return FA_OK;
+}
+
+// PEER transport, start of a call: publish this rank's K/V in its window (epoch e) and tell every peer.
+int peer_publish_kv(Ring *r, const void *K, const void *V, size_t tile_bytes, uint32_t e) {
+  cudaStream_t cs = r->comm_stream;
+  for (int p = 0; p < r->world; ++p)  // every peer has finished reading the previous epoch
+    if (p != r->rank) {
+      int rc = flag_wait(cs, r->flags + kFlagKvDone + p, e - 1);
+      if (rc != FA_OK) return rc;
+    }
+  FA_CUDA_CHECK(cudaMemcpyAsync(r->data, K, tile_bytes, cudaMemcpyDeviceToDevice, cs));
+  FA_CUDA_CHECK(cudaMemcpyAsync(r->data + tile_bytes, V, tile_bytes, cudaMemcpyDeviceToDevice, cs));
+  for (int p = 0; p < r->world; ++p)
+    if (p != r->rank) {
+      int rc = flag_write(cs, r->peer_flags[p] + kFlagKvReady + r->rank, e, r);
+      if (rc != FA_OK) return rc;
+    }
+  return FA_OK;
+}
+
+// PEER transport: pull the part of rank src's K/V that block b needs into `slot` ([K | V], chunk layout)
+int peer_pull_kv(Ring *r, const Block &b, char *slot, size_t tile_bytes, int n_local, int D, int H, uint32_t e) {
+  cudaStream_t cs = r->comm_stream;
+  int rc = flag_wait(cs, r->flags + kFlagKvReady + b.src, e);
+  if (rc != FA_OK) return rc;
+  const char *src = r->peer_data[b.src];
+  if ((rc = copy_rows(slot, src, n_local, D, H, b.k_off, b.k_rows, cs)) != FA_OK) return rc;
+  if ((rc = copy_rows(slot + tile_bytes, src + tile_bytes, n_local, D, H, b.k_off, b.k_rows, cs)) != FA_OK) return rc;
+  return flag_write(cs, r->peer_flags[b.src] + kFlagKvDone + r->rank, e, r);
 }
 
 }  // namespace
@@ -209,47 +423,61 @@ int fa_ring_get_unique_id(void *out, int bytes) {
   return FA_OK;
 }
 
-int fa_ring_create(void **ring_out, const void *unique_id, int rank, int world, int device) {
-  FA_REQUIRE(ring_out && unique_id && world >= 1 && rank >= 0 && rank < world, "bad ring arguments");
+int fa_ring_create_ex(void **ring_out, const void *unique_id, int rank, int world, int device, int transport) {
+  FA_REQUIRE(ring_out && unique_id && world >= 1 && world <= kRingMaxWorld && rank >= 0 && rank < world,
+             "bad ring arguments (world must be 1..%d)", kRingMaxWorld);
+  FA_REQUIRE(transport >= FA_RING_TRANSPORT_AUTO && transport <= FA_RING_TRANSPORT_PEER, "unknown ring transport %d", transport);
   NcclApi *api = nccl();
   if (!api) return set_error(FA_ERR_NCCL, "libnccl.so.2 could not be loaded");
   FA_CUDA_CHECK(cudaSetDevice(device));
   Ring *r = new Ring();
   r->rank = rank; r->world = world; r->device = device;
+  auto fail = [&](int rc) { ring_free(r); return rc; };
   NcclUniqueId id;
   memcpy(&id, unique_id, sizeof(id));
-  int rc = api->CommInitRank(&r->comm, world, id, rank);
-  if (rc != 0) {
-    delete r;
-    return set_error(FA_ERR_NCCL, "ncclCommInitRank failed: %s", api->GetErrorString ? api->GetErrorString(rc) : "?");
+  int nrc = api->CommInitRank(&r->comm, world, id, rank);
+  if (nrc != 0) {
+    r->comm = nullptr;
+    return fail(nccl_error("ncclCommInitRank", nrc));
   }
-  FA_CUDA_CHECK(cudaStreamCreateWithFlags(&r->comm_stream, cudaStreamNonBlocking));
-  FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->inputs_ready, cudaEventDisableTiming));
-  for (int i = 0; i < 2; ++i) {
-    FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->recv_done[i], cudaEventDisableTiming));
-    FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->compute_done[i], cudaEventDisableTiming));
-    FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->add_done[i], cudaEventDisableTiming));
-    FA_CUDA_CHECK(cudaEventCreateWithFlags(&r->acc_recv_done[i], cudaEventDisableTiming));
+  int rc = ring_init_streams(r);
+  if (rc != FA_OK) return fail(rc);
+  if (cudaMalloc(&r->xchg, sizeof(IpcBlob) * kRingMaxWorld) != cudaSuccess)
+    return fail(set_error(FA_ERR_CUDA, "cudaMalloc of the exchange buffer failed"));
+  r->transport = transport == FA_RING_TRANSPORT_AUTO ? FA_RING_TRANSPORT_NCCL : transport;
+  if (world > 1 && (transport == FA_RING_TRANSPORT_AUTO || transport == FA_RING_TRANSPORT_PEER)) {
+    // try to set the peer transport up; the outcome is agreed by all ranks inside map_peer_windows
+    const MemOps *m = memops();
+    const bool have_ops = m->wait && m->write;
+    bool ok = false;
+    if (have_ops) (void)ring_alloc_flags(r);
+    rc = map_peer_windows(r, have_ops ? r->flags : nullptr, reinterpret_cast<void **>(r->peer_flags), &ok);
+    if (rc != FA_OK) return fail(rc);
+    if (ok) {
+      r->transport = FA_RING_TRANSPORT_PEER;
+    } else if (transport == FA_RING_TRANSPORT_PEER) {
+      return fail(set_error(FA_ERR_UNSUPPORTED, "the peer transport (CUDA IPC + stream memory operations) is not available on every rank"));
+    }
   }
   *ring_out = r;
   return FA_OK;
 }
 
+int fa_ring_create(void **ring_out, const void *unique_id, int rank, int world, int device) {
+  return fa_ring_create_ex(ring_out, unique_id, rank, world, device, FA_RING_TRANSPORT_AUTO);
+}
+
+int fa_ring_transport(void *ring) {
+  Ring *r = reinterpret_cast<Ring *>(ring);
+  FA_REQUIRE(r, "null ring");
+  return r->transport;
+}
+
 int fa_ring_destroy(void *ring) {
   Ring *r = reinterpret_cast<Ring *>(ring);
   if (!r) return FA_OK;
-  cudaSetDevice(r->device);
-  if (r->comm_stream) cudaStreamSynchronize(r->comm_stream);
-  if (r->comm && nccl() && nccl()->CommDestroy) nccl()->CommDestroy(r->comm);
-  if (r->comm_stream) cudaStreamDestroy(r->comm_stream);
-  if (r->inputs_ready) cudaEventDestroy(r->inputs_ready);
-  for (int i = 0; i < 2; ++i) {
-    if (r->recv_done[i]) cudaEventDestroy(r->recv_done[i]);
-    if (r->compute_done[i]) cudaEventDestroy(r->compute_done[i]);
-    if (r->add_done[i]) cudaEventDestroy(r->add_done[i]);
-    if (r->acc_recv_done[i]) cudaEventDestroy(r->acc_recv_done[i]);
-  }
-  delete r;
+  if (r->group) return set_error(FA_ERR_INVALID, "this ring belongs to an fa_mgpu group: destroy the group");
+  ring_free(r);
   return FA_OK;
 }
 
@@ -278,23 +506,19 @@ int fa_ring_local_rows(int rank, int world, int n_local, int is_causal, int64_t 
   return FA_OK;
 }
 
-size_t fa_ring_workspace_bytes(int n_local, int D, int H, int dtype) {
+// Forward workspace: [receive slots: 2 x (K | V), or world x (K | V) for NCCL_GATHER] [O_acc fp32] [L_acc fp32]
+size_t fa_ring_workspace_bytes_ex(int world, int transport, int n_local, int D, int H, int dtype) {
   (void)dtype;
-  if (n_local < 1 || H < 1 || D < 1) return 0;
+  if (n_local < 1 || H < 1 || D < 1 || world < 1) return 0;
   const size_t tile = (size_t)H * n_local * D;
-  size_t bytes = 2 * (2 * tile * 2)   // two receive slots, each K | V
-                 + tile * 2            // partial O (16-bit)
-                 + tile * 4            // O accumulator (fp32)
-                 + 3 * (size_t)H * n_local * 4;  // partial L, two L accumulators (ping-pong)
-  return bytes + 1024;
+  const size_t slots = transport == FA_RING_TRANSPORT_NCCL_GATHER ? (size_t)world : 2;
+  return slots * (2 * tile * 2) + tile * 4 + (size_t)H * n_local * 4 + 1024;
 }
-
-// Workspace of the all-gather forward mode: room for every rank's K and V instead of two receive slots.
+size_t fa_ring_workspace_bytes(int n_local, int D, int H, int dtype) {
+  return fa_ring_workspace_bytes_ex(2, FA_RING_TRANSPORT_AUTO, n_local, D, H, dtype);
+}
 size_t fa_ring_workspace_bytes_gather(int world, int n_local, int D, int H, int dtype) {
-  const size_t base = fa_ring_workspace_bytes(n_local, D, H, dtype);
-  if (base == 0 || world < 1) return 0;
-  const size_t tile = (size_t)H * n_local * D;
-  return base - 2 * (2 * tile * 2) + 2 * (size_t)world * tile * 2;
+  return fa_ring_workspace_bytes_ex(world, FA_RING_TRANSPORT_NCCL_GATHER, n_local, D, H, dtype);
 }
 
 int fa_ring_attention_forward(void *ring, const void *Q, const void *K, const void *V, void *O, float *L_out,
@@ -305,86 +529,89 @@ int fa_ring_attention_forward(void *ring, const void *Q, const void *K, const vo
   FA_REQUIRE(D == 64 || D == 128, "D must be 64 or 128 (got %d)", D);
   FA_REQUIRE(!is_causal || n_local % 2 == 0, "causal ring attention needs an even n_local");
   FA_REQUIRE(n_local % 8 == 0, "n_local must be a multiple of 8");
-  const size_t need = fa_ring_workspace_bytes(n_local, D, H, dtype);
-  if (!workspace || workspace_bytes < need)
-    return set_error(FA_ERR_WORKSPACE, "ring workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
-  NcclApi *api = nccl();
-  if (!api) return set_error(FA_ERR_NCCL, "libnccl.so.2 could not be loaded");
-  cudaStream_t st = (cudaStream_t)stream_;
   const int P = r->world;
+  const size_t need = fa_ring_workspace_bytes_ex(P, r->transport, n_local, D, H, dtype);
+  if (!workspace || workspace_bytes < need)
+    return set_error(FA_ERR_WORKSPACE, "ring workspace too small for transport %d: need %zu bytes, got %zu",
+                     r->transport, need, workspace_bytes);
+  NcclApi *api = nccl();
+  if (P > 1 && r->transport != FA_RING_TRANSPORT_PEER && !api) return set_error(FA_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  FA_CUDA_CHECK(cudaSetDevice(r->device));
+  cudaStream_t st = (cudaStream_t)stream_;
   const size_t tile_elems = (size_t)H * n_local * D;
   const size_t tile_bytes = tile_elems * 2;
   char *ws = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
-  // All-gather mode (opt-in: FA_RING_GATHER=1 and a workspace of fa_ring_workspace_bytes_gather):
-  // for steps whose compute is shorter than their K/V hand-off (medium N on many GPUs) the ring is
-  // bound by its per-step transfer; here every rank's K/V is gathered once (ncclAllGather on the side
-  // stream, under the local block) and the P - 1 remote blocks then run back to back.
-  static const int gather_env = [] { const char *e = getenv("FA_RING_GATHER"); return e ? atoi(e) : 0; }();
-  const bool gather = gather_env != 0 && P > 1 && api->AllGather != nullptr &&
-                      workspace_bytes >= fa_ring_workspace_bytes_gather(P, n_local, D, H, dtype);
-  const size_t kv_area = gather ? 2 * (size_t)P * tile_bytes : 4 * tile_bytes;  // [K of all ranks | V of all ranks] or 2 slots
+  const bool gather = r->transport == FA_RING_TRANSPORT_NCCL_GATHER && P > 1;
+  const size_t kv_area = (gather ? (size_t)P : 2) * 2 * tile_bytes;
   char *slot[2] = {ws, ws + 2 * tile_bytes};
   char *k_all = ws, *v_all = ws + (size_t)P * tile_bytes;
-  uint16_t *o_part = reinterpret_cast<uint16_t *>(ws + kv_area);
-  float *o_acc = reinterpret_cast<float *>(ws + kv_area + tile_bytes);
-  float *l_part = reinterpret_cast<float *>(ws + kv_area + tile_bytes + tile_elems * 4);
-  float *l_acc[2] = {l_part + (size_t)H * n_local, l_part + 2 * (size_t)H * n_local};
-  int l_cur[2] = {0, 0};  // which L accumulator holds the current value, per half
+  float *o_acc = reinterpret_cast<float *>(ws + kv_area);
+  float *l_acc = reinterpret_cast<float *>(ws + kv_area + tile_elems * 4);
   const int next = (r->rank + 1) % P, prev = (r->rank - 1 + P) % P;
   const int64_t hs = (int64_t)n_local * D;
+  const int c = n_local / 2;
 
-  FA_CUDA_CHECK(cudaEventRecord(r->inputs_ready, st));
-  // which local rows have received a contribution so far (for the first/last flags per row range)
-  bool touched[2] = {false, false};  // [first half, second half] when causal; [all, -] otherwise
-  // ---- local work of ring step s on the chunk (curK, curV) of rank (rank - s) mod P ----
+  // ---- local work of ring step s on the chunk (curK, curV) of rank (rank - s) mod P: ONE launch,
+  //      the running (O, L) is folded in the kernel epilogue ----
   auto do_step = [&](int s, const void *curK, const void *curV) -> int {
     Block b;
     ring_plan(r->rank, P, s, n_local, is_causal, &b);
     const uint16_t *q = reinterpret_cast<const uint16_t *>(Q) + (int64_t)b.q_off * D;
     const uint16_t *k = reinterpret_cast<const uint16_t *>(curK) + (int64_t)b.k_off * D;
     const uint16_t *v = reinterpret_cast<const uint16_t *>(curV) + (int64_t)b.k_off * D;
-    int rc = launch_fwd_tc_rect(q, k, v, o_part + (int64_t)b.q_off * D, l_part + b.q_off, b.q_rows, b.k_rows, D, scale,
-                                (int64_t)H * hs, hs, (int64_t)H * hs, hs, b.causal, 1, H, dtype, st);
+    FwdMerge m;
+    m.O_acc = o_acc + (int64_t)b.q_off * D;
+    m.L_acc = l_acc + b.q_off;
+    if (!is_causal) {
+      m.lo = m.hi = merge_mode(s == 0, s == P - 1);
+      m.half_rows = 0;
+    } else {
+      // first zig-zag chunk (local rows < c): touched at steps 0..rank; second chunk: at every step
+      const int lo = merge_mode(s == 0, s == r->rank), hi = merge_mode(s == 0, s == P - 1);
+      if (b.q_off == 0) { m.lo = lo; m.hi = hi; m.half_rows = c; }
+      else { m.lo = m.hi = hi; m.half_rows = 0; }
+    }
+    return launch_fwd_tc_rect(q, k, v, reinterpret_cast<uint16_t *>(O) + (int64_t)b.q_off * D,
+                              L_out ? L_out + b.q_off : nullptr, b.q_rows, b.k_rows, D, scale, (int64_t)H * hs, hs,
+                              (int64_t)H * hs, hs, b.causal, 1, H, dtype, st, &m);
+  };
+  if (P == 1) return do_step(0, K, V);
+
+  FA_CUDA_CHECK(cudaEventRecord(r->inputs_ready, st));
+  // the comm stream's work of the previous call on this ring is ordered before this call's
+  FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->inputs_ready, 0));
+
+  if (r->transport == FA_RING_TRANSPORT_PEER) {
+    int rc = ring_ensure_window(r, 2 * tile_bytes);
     if (rc != FA_OK) return rc;
-    // merge per half so that "first contribution" / "last contribution" are uniform within a launch
-    const int halves = is_causal ? 2 : 1;
-    const int hrows = is_causal ? n_local / 2 : n_local;
-    for (int hf = 0; hf < halves; ++hf) {
-      const int lo = hf * hrows, hi = lo + hrows;
-      if (b.q_off >= hi || b.q_off + b.q_rows <= lo) continue;  // this half is not in the block
-      // does any later step touch this half?  (causal: first half is only touched while src <= rank)
-      bool later = false;
-      for (int s2 = s + 1; s2 < P; ++s2) {
-        Block b2;
-        ring_plan(r->rank, P, s2, n_local, is_causal, &b2);
-        if (!(b2.q_off >= hi || b2.q_off + b2.q_rows <= lo)) later = true;
+    const uint32_t e = ++r->epoch;
+    if ((rc = peer_publish_kv(r, K, V, tile_bytes, e)) != FA_OK) return rc;
+    for (int s = 0; s < P; ++s) {
+      if (s + 1 < P) {  // fetch the chunk of step s + 1 while step s computes
+        Block nb;
+        ring_plan(r->rank, P, s + 1, n_local, is_causal, &nb);
+        // slot (s+1)&1 was read by step s-1
+        if (s >= 1) FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->compute_done[(s - 1) & 1], 0));
+        if ((rc = peer_pull_kv(r, nb, slot[(s + 1) & 1], tile_bytes, n_local, D, H, e)) != FA_OK) return rc;
+        FA_CUDA_CHECK(cudaEventRecord(r->recv_done[(s + 1) & 1], r->comm_stream));
       }
-      const int64_t work = (int64_t)hrows * (D / 8);
-      dim3 grid((unsigned)((work + 255) / 256), H);
-      if (dtype == FA_DTYPE_BF16)
-        ring_merge_kernel<1><<<grid, 256, 0, st>>>(o_acc, l_acc[l_cur[hf]], l_acc[l_cur[hf] ^ 1], o_part, l_part, reinterpret_cast<uint16_t *>(O), L_out,
-                                                   n_local, D, lo, hrows, !touched[hf], !later);
-      else
-        ring_merge_kernel<0><<<grid, 256, 0, st>>>(o_acc, l_acc[l_cur[hf]], l_acc[l_cur[hf] ^ 1], o_part, l_part, reinterpret_cast<uint16_t *>(O), L_out,
-                                                   n_local, D, lo, hrows, !touched[hf], !later);
-      FA_CUDA_CHECK(cudaGetLastError());
-      count_launch();
-      touched[hf] = true;
-      l_cur[hf] ^= 1;
+      if (s > 0) FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->recv_done[s & 1], 0));
+      rc = s == 0 ? do_step(0, K, V) : do_step(s, slot[s & 1], slot[s & 1] + tile_bytes);
+      if (rc != FA_OK) return rc;
+      FA_CUDA_CHECK(cudaEventRecord(r->compute_done[s & 1], st));
     }
     return FA_OK;
-  };
+  }
 
   if (gather) {
-    // the previous call's readers of the gather area are ordered before this one by the stream: `st`
-    // reached inputs_ready only after them
-    FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->inputs_ready, 0));
-    FA_NCCL_CHECK(api->GroupStart());
-    FA_NCCL_CHECK(api->AllGather(K, k_all, tile_bytes, kNcclUint8, r->comm, r->comm_stream));
-    FA_NCCL_CHECK(api->AllGather(V, v_all, tile_bytes, kNcclUint8, r->comm, r->comm_stream));
-    FA_NCCL_CHECK(api->GroupEnd());
+    int rc = nccl_group(api, [&]() -> int {
+      FA_NCCL_CHECK(api->AllGather(K, k_all, tile_bytes, kNcclUint8, r->comm, r->comm_stream));
+      FA_NCCL_CHECK(api->AllGather(V, v_all, tile_bytes, kNcclUint8, r->comm, r->comm_stream));
+      return FA_OK;
+    });
+    if (rc != FA_OK) return rc;
     FA_CUDA_CHECK(cudaEventRecord(r->recv_done[0], r->comm_stream));
-    int rc = do_step(0, K, V);  // the local block runs under the gather
+    rc = do_step(0, K, V);  // the local block runs under the gather
     if (rc != FA_OK) return rc;
     FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->recv_done[0], 0));
     for (int s = 1; s < P; ++s) {
@@ -395,20 +622,21 @@ int fa_ring_attention_forward(void *ring, const void *Q, const void *K, const vo
     return FA_OK;
   }
 
+  // ---- NCCL send/recv ring: the chunk we hold travels on to the next rank while we work on it ----
   const void *curK = K, *curV = V;
   for (int s = 0; s < P; ++s) {
     if (s + 1 < P) {
-      // ---- ship the chunk we hold to the next rank while we work on it ----
-      if (s == 0) FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->inputs_ready, 0));
       // the slot we are about to overwrite was the chunk step s-1 computed on (s >= 2 only)
       if (s >= 2) FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->compute_done[(s - 1) & 1], 0));
       char *dst = slot[s & 1];
-      FA_NCCL_CHECK(api->GroupStart());
-      FA_NCCL_CHECK(api->Send(curK, tile_bytes, kNcclUint8, next, r->comm, r->comm_stream));
-      FA_NCCL_CHECK(api->Send(curV, tile_bytes, kNcclUint8, next, r->comm, r->comm_stream));
-      FA_NCCL_CHECK(api->Recv(dst, tile_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-      FA_NCCL_CHECK(api->Recv(dst + tile_bytes, tile_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-      FA_NCCL_CHECK(api->GroupEnd());
+      int rc = nccl_group(api, [&]() -> int {
+        FA_NCCL_CHECK(api->Send(curK, tile_bytes, kNcclUint8, next, r->comm, r->comm_stream));
+        FA_NCCL_CHECK(api->Send(curV, tile_bytes, kNcclUint8, next, r->comm, r->comm_stream));
+        FA_NCCL_CHECK(api->Recv(dst, tile_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+        FA_NCCL_CHECK(api->Recv(dst + tile_bytes, tile_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
+        return FA_OK;
+      });
+      if (rc != FA_OK) return rc;
       FA_CUDA_CHECK(cudaEventRecord(r->recv_done[s & 1], r->comm_stream));
     }
     int rc = do_step(s, curK, curV);
@@ -423,13 +651,15 @@ int fa_ring_attention_forward(void *ring, const void *Q, const void *K, const vo
   return FA_OK;
 }
 
+// Backward workspace.  NCCL: [2 K|V slots][tmp dK|dV][2 outgoing accumulators][incoming accumulator][delta];
+// PEER: the outgoing accumulators live in the peer-visible window instead.
 size_t fa_ring_workspace_bytes_backward(int n_local, int D, int H, int dtype) {
   (void)dtype;
   if (n_local < 1 || H < 1 || D < 1) return 0;
   const size_t tile = (size_t)H * n_local * D;
   size_t bytes = 2 * (2 * tile * 2)        // two K|V receive slots (16-bit)
                  + 2 * tile * 4            // this step's dK|dV block (fp32)
-                 + 2 * (2 * tile * 4)      // two outgoing dK|dV accumulators
+                 + 2 * (2 * tile * 4)      // two outgoing dK|dV accumulators (NCCL transport)
                  + 2 * tile * 4            // incoming dK|dV accumulator
                  + (size_t)H * n_local * 4;  // delta
   return bytes + 1024;
@@ -452,10 +682,12 @@ int fa_ring_attention_backward(void *ring, const void *Q, const void *K, const v
   const size_t need = fa_ring_workspace_bytes_backward(n_local, D, H, dtype);
   if (!workspace || workspace_bytes < need)
     return set_error(FA_ERR_WORKSPACE, "ring backward workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
-  NcclApi *api = nccl();
-  if (!api) return set_error(FA_ERR_NCCL, "libnccl.so.2 could not be loaded");
-  cudaStream_t st = (cudaStream_t)stream_;
   const int P = r->world;
+  const bool peer = r->transport == FA_RING_TRANSPORT_PEER && P > 1;
+  NcclApi *api = nccl();
+  if (P > 1 && !peer && !api) return set_error(FA_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  FA_CUDA_CHECK(cudaSetDevice(r->device));
+  cudaStream_t st = (cudaStream_t)stream_, cs = r->comm_stream;
   const size_t tile_elems = (size_t)H * n_local * D;
   const size_t kv_bytes = tile_elems * 2, g_bytes = tile_elems * 4;
   char *ws = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~(uintptr_t)255);
@@ -468,55 +700,120 @@ int fa_ring_attention_backward(void *ring, const void *Q, const void *K, const v
   const int64_t hs = (int64_t)n_local * D;
   int rc = launch_bwd_delta(O, dO, delta, n_local, D, (int64_t)H * hs, hs, 1, H, dtype, st);
   if (rc != FA_OK) return rc;
-  FA_CUDA_CHECK(cudaEventRecord(r->inputs_ready, st));
-  const void *curK = K, *curV = V;
-  if (P > 1) {  // A(0): our own chunk starts travelling
-    FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->inputs_ready, 0));
-    FA_NCCL_CHECK(api->GroupStart());
-    FA_NCCL_CHECK(api->Send(curK, kv_bytes, kNcclUint8, next, r->comm, r->comm_stream));
-    FA_NCCL_CHECK(api->Send(curV, kv_bytes, kNcclUint8, next, r->comm, r->comm_stream));
-    FA_NCCL_CHECK(api->Recv(slot[0], kv_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-    FA_NCCL_CHECK(api->Recv(slot[0] + kv_bytes, kv_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-    FA_NCCL_CHECK(api->GroupEnd());
-    FA_CUDA_CHECK(cudaEventRecord(r->recv_done[0], r->comm_stream));
-  }
-  for (int s = 0; s < P; ++s) {
+
+  auto block_backward = [&](int s, const void *curK, const void *curV, Block *b_out) -> int {
     Block b;
     ring_plan(r->rank, P, s, n_local, is_causal, &b);
+    *b_out = b;
     const uint16_t *q = reinterpret_cast<const uint16_t *>(Q) + (int64_t)b.q_off * D;
     const uint16_t *g = reinterpret_cast<const uint16_t *>(dO) + (int64_t)b.q_off * D;
     const uint16_t *k = reinterpret_cast<const uint16_t *>(curK) + (int64_t)b.k_off * D;
     const uint16_t *v = reinterpret_cast<const uint16_t *>(curV) + (int64_t)b.k_off * D;
     float *blk_dk = (P == 1 ? dK : tmp) + (int64_t)b.k_off * D;
     float *blk_dv = (P == 1 ? dV : tmp + tile_elems) + (int64_t)b.k_off * D;
-    rc = launch_bwd_tc_rect(q, k, v, g, L + b.q_off, delta + b.q_off, dQ + (int64_t)b.q_off * D, blk_dk, blk_dv, b.q_rows,
-                            b.k_rows, D, scale, (int64_t)H * hs, hs, (int64_t)H * hs, hs, b.causal, s > 0, 1, H, dtype, st);
+    return launch_bwd_tc_rect(q, k, v, g, L + b.q_off, delta + b.q_off, dQ + (int64_t)b.q_off * D, blk_dk, blk_dv, b.q_rows,
+                              b.k_rows, D, scale, (int64_t)H * hs, hs, (int64_t)H * hs, hs, b.causal, s > 0, 1, H, dtype, st);
+  };
+  auto add_block = [&](float *out, const Block &b, bool has_in) -> int {
+    const int64_t vecs = (int64_t)tile_elems / 4;
+    dim3 grid((unsigned)((vecs + 255) / 256), 2);
+    ring_dkv_add_kernel<<<grid, 256, 0, st>>>(out, acc_in, tmp, (int64_t)tile_elems, n_local, D, b.k_off, b.k_rows, has_in);
+    FA_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    return FA_OK;
+  };
+  if (P == 1) {
+    Block b;
+    return block_backward(0, K, V, &b);
+  }
+  FA_CUDA_CHECK(cudaEventRecord(r->inputs_ready, st));
+  FA_CUDA_CHECK(cudaStreamWaitEvent(cs, r->inputs_ready, 0));
+
+  if (peer) {
+    // window: [K | V] [acc_out 0: dK | dV] [acc_out 1: dK | dV]
+    if ((rc = ring_ensure_window(r, 2 * kv_bytes + 4 * g_bytes)) != FA_OK) return rc;
+    const uint32_t e = ++r->epoch;
+    const size_t acc_off[2] = {2 * kv_bytes, 2 * kv_bytes + 2 * g_bytes};
+    float *wacc[2] = {reinterpret_cast<float *>(r->data + acc_off[0]), reinterpret_cast<float *>(r->data + acc_off[1])};
+    if ((rc = peer_publish_kv(r, K, V, kv_bytes, e)) != FA_OK) return rc;
+    Block nb;
+    ring_plan(r->rank, P, 1, n_local, is_causal, &nb);
+    if ((rc = peer_pull_kv(r, nb, slot[1], kv_bytes, n_local, D, H, e)) != FA_OK) return rc;
+    FA_CUDA_CHECK(cudaEventRecord(r->recv_done[1], cs));
+    for (int s = 0; s < P; ++s) {
+      Block b;
+      if (s > 0) FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->recv_done[s & 1], 0));
+      rc = s == 0 ? block_backward(0, K, V, &b) : block_backward(s, slot[s & 1], slot[s & 1] + kv_bytes, &b);
+      if (rc != FA_OK) return rc;
+      FA_CUDA_CHECK(cudaEventRecord(r->compute_done[s & 1], st));
+      // ---- dK/dV accumulator of the chunk we hold: incoming sum (pulled from prev) + our block ----
+      if (s > 0) FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->acc_recv_done[s & 1], 0));
+      const uint32_t k_pub = r->acc_pub + 1;  // this publication's sequence number
+      if (k_pub > 2 && (rc = flag_wait(st, r->flags + kFlagAccDone, k_pub - 2)) != FA_OK) return rc;  // slot reuse
+      if ((rc = add_block(wacc[k_pub & 1], b, s > 0)) != FA_OK) return rc;
+      FA_CUDA_CHECK(cudaEventRecord(r->add_done[s & 1], st));
+      if ((rc = flag_write(st, r->peer_flags[next] + kFlagAccReady, k_pub, r)) != FA_OK) return rc;
+      r->acc_pub = k_pub;
+      // ---- comm stream: pull what prev published at its step s (its k-th publication, k = ours) ----
+      const uint32_t k_pull = ++r->acc_pull;
+      if ((rc = flag_wait(cs, r->flags + kFlagAccReady, k_pull)) != FA_OK) return rc;
+      const char *src_acc = r->peer_data[prev] + acc_off[k_pull & 1];
+      if (s + 1 < P) {
+        FA_CUDA_CHECK(cudaStreamWaitEvent(cs, r->add_done[s & 1], 0));  // acc_in was read by this step's add
+        FA_CUDA_CHECK(cudaMemcpyAsync(acc_in, src_acc, 2 * g_bytes, cudaMemcpyDeviceToDevice, cs));
+      } else {  // last hop: the finished gradients of our own chunk come home
+        FA_CUDA_CHECK(cudaMemcpyAsync(dK, src_acc, g_bytes, cudaMemcpyDeviceToDevice, cs));
+        FA_CUDA_CHECK(cudaMemcpyAsync(dV, src_acc + g_bytes, g_bytes, cudaMemcpyDeviceToDevice, cs));
+      }
+      if ((rc = flag_write(cs, r->peer_flags[prev] + kFlagAccDone, k_pull, r)) != FA_OK) return rc;
+      FA_CUDA_CHECK(cudaEventRecord(r->acc_recv_done[(s + 1) & 1], cs));
+      // ---- K/V of step s + 2 into the slot step s has just finished with ----
+      if (s + 2 < P) {
+        ring_plan(r->rank, P, s + 2, n_local, is_causal, &nb);
+        FA_CUDA_CHECK(cudaStreamWaitEvent(cs, r->compute_done[s & 1], 0));
+        if ((rc = peer_pull_kv(r, nb, slot[s & 1], kv_bytes, n_local, D, H, e)) != FA_OK) return rc;
+        FA_CUDA_CHECK(cudaEventRecord(r->recv_done[s & 1], cs));
+      }
+    }
+    FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->acc_recv_done[P & 1], 0));
+    return FA_OK;
+  }
+
+  // ---- NCCL transport ----
+  const void *curK = K, *curV = V;
+  {  // A(0): our own chunk starts travelling
+    rc = nccl_group(api, [&]() -> int {
+      FA_NCCL_CHECK(api->Send(curK, kv_bytes, kNcclUint8, next, r->comm, cs));
+      FA_NCCL_CHECK(api->Send(curV, kv_bytes, kNcclUint8, next, r->comm, cs));
+      FA_NCCL_CHECK(api->Recv(slot[0], kv_bytes, kNcclUint8, prev, r->comm, cs));
+      FA_NCCL_CHECK(api->Recv(slot[0] + kv_bytes, kv_bytes, kNcclUint8, prev, r->comm, cs));
+      return FA_OK;
+    });
     if (rc != FA_OK) return rc;
-    if (P == 1) break;
+    FA_CUDA_CHECK(cudaEventRecord(r->recv_done[0], cs));
+  }
+  for (int s = 0; s < P; ++s) {
+    Block b;
+    if ((rc = block_backward(s, curK, curV, &b)) != FA_OK) return rc;
     // ---- dK/dV accumulator of the chunk we hold: add our block, pass it on ----
     if (s > 0) FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->acc_recv_done[s & 1], 0));
-    {
-      const int64_t vecs = (int64_t)tile_elems / 4;
-      dim3 grid((unsigned)((vecs + 255) / 256), 2);
-      ring_dkv_add_kernel<<<grid, 256, 0, st>>>(acc_out[s & 1], acc_in, tmp, (int64_t)tile_elems, n_local, D, b.k_off,
-                                                b.k_rows, s > 0);
-      FA_CUDA_CHECK(cudaGetLastError());
-      count_launch();
-    }
+    if ((rc = add_block(acc_out[s & 1], b, s > 0)) != FA_OK) return rc;
     FA_CUDA_CHECK(cudaEventRecord(r->add_done[s & 1], st));
-    FA_CUDA_CHECK(cudaStreamWaitEvent(r->comm_stream, r->add_done[s & 1], 0));
-    FA_NCCL_CHECK(api->GroupStart());
-    FA_NCCL_CHECK(api->Send(acc_out[s & 1], g_bytes, kNcclUint8, next, r->comm, r->comm_stream));
-    FA_NCCL_CHECK(api->Send(acc_out[s & 1] + tile_elems, g_bytes, kNcclUint8, next, r->comm, r->comm_stream));
-    if (s + 1 < P) {
-      FA_NCCL_CHECK(api->Recv(acc_in, g_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-      FA_NCCL_CHECK(api->Recv(acc_in + tile_elems, g_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-    } else {  // last hop: the finished gradients of our own chunk come home
-      FA_NCCL_CHECK(api->Recv(dK, g_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-      FA_NCCL_CHECK(api->Recv(dV, g_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-    }
-    FA_NCCL_CHECK(api->GroupEnd());
-    FA_CUDA_CHECK(cudaEventRecord(r->acc_recv_done[(s + 1) & 1], r->comm_stream));
+    FA_CUDA_CHECK(cudaStreamWaitEvent(cs, r->add_done[s & 1], 0));
+    rc = nccl_group(api, [&]() -> int {
+      FA_NCCL_CHECK(api->Send(acc_out[s & 1], g_bytes, kNcclUint8, next, r->comm, cs));
+      FA_NCCL_CHECK(api->Send(acc_out[s & 1] + tile_elems, g_bytes, kNcclUint8, next, r->comm, cs));
+      if (s + 1 < P) {
+        FA_NCCL_CHECK(api->Recv(acc_in, g_bytes, kNcclUint8, prev, r->comm, cs));
+        FA_NCCL_CHECK(api->Recv(acc_in + tile_elems, g_bytes, kNcclUint8, prev, r->comm, cs));
+      } else {  // last hop: the finished gradients of our own chunk come home
+        FA_NCCL_CHECK(api->Recv(dK, g_bytes, kNcclUint8, prev, r->comm, cs));
+        FA_NCCL_CHECK(api->Recv(dV, g_bytes, kNcclUint8, prev, r->comm, cs));
+      }
+      return FA_OK;
+    });
+    if (rc != FA_OK) return rc;
+    FA_CUDA_CHECK(cudaEventRecord(r->acc_recv_done[(s + 1) & 1], cs));
     // ---- K/V: switch to the chunk that arrived, forward it if somebody still needs it ----
     if (s + 1 < P) {
       FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->recv_done[s & 1], 0));
@@ -524,17 +821,19 @@ int fa_ring_attention_backward(void *ring, const void *Q, const void *K, const v
       curV = slot[s & 1] + kv_bytes;
       if (s + 2 < P) {  // the other slot was read by step s, which the comm stream has already waited for
         char *dst = slot[(s + 1) & 1];
-        FA_NCCL_CHECK(api->GroupStart());
-        FA_NCCL_CHECK(api->Send(curK, kv_bytes, kNcclUint8, next, r->comm, r->comm_stream));
-        FA_NCCL_CHECK(api->Send(curV, kv_bytes, kNcclUint8, next, r->comm, r->comm_stream));
-        FA_NCCL_CHECK(api->Recv(dst, kv_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-        FA_NCCL_CHECK(api->Recv(dst + kv_bytes, kv_bytes, kNcclUint8, prev, r->comm, r->comm_stream));
-        FA_NCCL_CHECK(api->GroupEnd());
-        FA_CUDA_CHECK(cudaEventRecord(r->recv_done[(s + 1) & 1], r->comm_stream));
+        rc = nccl_group(api, [&]() -> int {
+          FA_NCCL_CHECK(api->Send(curK, kv_bytes, kNcclUint8, next, r->comm, cs));
+          FA_NCCL_CHECK(api->Send(curV, kv_bytes, kNcclUint8, next, r->comm, cs));
+          FA_NCCL_CHECK(api->Recv(dst, kv_bytes, kNcclUint8, prev, r->comm, cs));
+          FA_NCCL_CHECK(api->Recv(dst + kv_bytes, kv_bytes, kNcclUint8, prev, r->comm, cs));
+          return FA_OK;
+        });
+        if (rc != FA_OK) return rc;
+        FA_CUDA_CHECK(cudaEventRecord(r->recv_done[(s + 1) & 1], cs));
       }
     }
   }
-  if (P > 1) FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->acc_recv_done[P & 1], 0));
+  FA_CUDA_CHECK(cudaStreamWaitEvent(st, r->acc_recv_done[P & 1], 0));
   return FA_OK;
 }
 

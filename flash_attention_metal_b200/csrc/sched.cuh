@@ -15,7 +15,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
+
+#include "fa_internal.h"
 
 namespace fa {
 
@@ -45,7 +46,7 @@ __device__ __forceinline__ BlockCoord decode_block(int group, int n_heads, int H
 // heads per dispatch group: all work equal -> 1; otherwise as many heads as stream <= 48 MB
 inline int dispatch_group(bool uneven_work, int64_t streamed_bytes_per_head, int n_heads) {
   if (!uneven_work) return 1;
-  static const int64_t budget_mb = [] { const char *e = getenv("FA_L2_GROUP_MB"); return e ? atoll(e) : 48ll; }();
+  const int64_t budget_mb = l2_group_mb();  // 48 by default (fa_internal.h)
   int64_t g = (budget_mb << 20) / (streamed_bytes_per_head > 0 ? streamed_bytes_per_head : 1);
   if (g < 1) g = 1;
   if (g > n_heads) g = n_heads;

@@ -125,23 +125,59 @@ int flash_attention_v4_half_rect(const void *Q, const void *K, const void *V, vo
                                  int64_t kv_batch_stride, int64_t kv_head_stride, float *L_out, int B,
                                  int H, int dtype, fa_stream_t stream);
 
+/* Rectangular backward (cross-attention gradients; SURVEY.md section 8 row f3, the reference's tail
+ * handling at kernels.metal:103-110, 658-662 is the only hook it has): gradients of
+ * attention(Q[Nq], K[Nk], V[Nk]), non-causal.  L is the log-sum-exp written by the forward over the
+ * FULL key range of each query row, `delta` = rowsum(O o dO) over the full output (fa_rowsum_delta);
+ * so the gradients of a softmax whose keys are processed in several chunks are the SUM of one call per
+ * chunk (dQ with acc_dq = 1 after the first; dK/dV per chunk).  dK/dV may both be NULL (dQ only) and dQ
+ * may be NULL (dK/dV only). */
+int flash_attention_backward_rect(const void *Q, const void *K, const void *V, const void *dO, const float *L,
+                                  const float *delta, float *dQ, float *dK, float *dV, int Nq, int Nk, int D,
+                                  float scale, int64_t q_batch_stride, int64_t q_head_stride,
+                                  int64_t kv_batch_stride, int64_t kv_head_stride, int acc_dq, int B, int H,
+                                  int dtype, fa_stream_t stream);
+/* delta[b, h, i] = sum_d O[b,h,i,d] * dO[b,h,i,d] (kernels.metal:983-990), addressed like L */
+int fa_rowsum_delta(const void *O, const void *dO, float *delta, int N, int D, int64_t batch_stride,
+                    int64_t head_stride, int B, int H, int dtype, fa_stream_t stream);
+
 /* ---- ring / context-parallel attention across the GPUs of one box (new; not in the
- * reference, BASELINE.json config 5).  One process per GPU.  Each rank holds n_local rows of
- * Q, K, V per head, contiguous [H, n_local, D].  Non-causal: rank r holds global rows
- * [r*n_local, (r+1)*n_local).  Causal: zig-zag -- with c = n_local/2, local rows [0,c) are
- * global chunk r and local rows [c,2c) are global chunk 2*world-1-r (fa_ring_local_rows), so
- * every rank does the same amount of unmasked work at every step.  K/V chunks rotate with
- * NCCL send/recv over NVLink on a side stream, overlapped with the local tile loop. */
+ * reference, BASELINE.json config 5).  One process per GPU (for one process driving all GPUs see
+ * fa_mgpu_* below).  Each rank holds n_local rows of Q, K, V per head, contiguous [H, n_local, D].
+ * Non-causal: rank r holds global rows [r*n_local, (r+1)*n_local).  Causal: zig-zag -- with
+ * c = n_local/2, local rows [0,c) are global chunk r and local rows [c,2c) are global chunk
+ * 2*world-1-r (fa_ring_local_rows), so every rank does the same amount of unmasked work at every
+ * step.  The partial result of a step is folded into the running (O, L) inside the forward kernel's
+ * epilogue: one launch per step.
+ *
+ * Transport -- how K/V chunks (and, backward, dK/dV accumulators) move between GPUs.  It is a property
+ * of the ring, fixed at creation and agreed by all ranks (every rank must pass the same value):
+ *   PEER        each rank exposes a window of device memory to its peers (CUDA IPC); chunks are
+ *               pulled straight from their owner by the copy engines over NVLink and ranks
+ *               synchronise through 32-bit flags with stream memory operations.  Uses no SMs.
+ *   NCCL        ncclSend/ncclRecv ring on a side stream.
+ *   NCCL_GATHER forward only: one ncclAllGather of every rank's K/V, then the remote blocks back to
+ *               back (needs the larger workspace of fa_ring_workspace_bytes_ex).
+ *   AUTO        PEER when every rank can set it up, else NCCL. */
 typedef void *fa_ring_t;
+enum {
+  FA_RING_TRANSPORT_AUTO = 0,
+  FA_RING_TRANSPORT_NCCL = 1,
+  FA_RING_TRANSPORT_NCCL_GATHER = 2,
+  FA_RING_TRANSPORT_PEER = 3
+};
 int fa_ring_unique_id_bytes(void);
 int fa_ring_get_unique_id(void *out, int bytes);            /* rank 0; ship the bytes to the others */
-int fa_ring_create(fa_ring_t *ring, const void *unique_id, int rank, int world, int device);
+int fa_ring_create(fa_ring_t *ring, const void *unique_id, int rank, int world, int device); /* AUTO */
+int fa_ring_create_ex(fa_ring_t *ring, const void *unique_id, int rank, int world, int device, int transport);
+int fa_ring_transport(fa_ring_t ring);                      /* the transport in effect (never AUTO) */
 int fa_ring_destroy(fa_ring_t ring);
-size_t fa_ring_workspace_bytes(int n_local, int D, int H, int dtype);
-/* Optional all-gather forward mode (set FA_RING_GATHER=1 and pass a workspace of at least this size):
- * every rank's K/V is gathered once under the local block and the remote blocks run back to back --
- * for medium N on many GPUs, where a ring step computes for less time than its K/V hand-off takes. */
-size_t fa_ring_workspace_bytes_gather(int world, int n_local, int D, int H, int dtype);
+/* forward workspace for a ring of `world` ranks using `transport` (as returned by fa_ring_transport) */
+size_t fa_ring_workspace_bytes_ex(int world, int transport, int n_local, int D, int H, int dtype);
+size_t fa_ring_workspace_bytes(int n_local, int D, int H, int dtype);             /* PEER and NCCL */
+size_t fa_ring_workspace_bytes_gather(int world, int n_local, int D, int H, int dtype); /* NCCL_GATHER */
+/* A workspace smaller than the ring's transport needs is an error (FA_ERR_WORKSPACE), never a silent
+ * change of algorithm.  Collective: every rank calls with the same shapes. */
 int fa_ring_attention_forward(fa_ring_t ring, const void *Q, const void *K, const void *V, void *O,
                               float *L_out, int n_local, int D, int H, float scale, int is_causal,
                               int dtype, void *workspace, size_t workspace_bytes, fa_stream_t stream);
@@ -158,6 +194,35 @@ int fa_ring_attention_backward(fa_ring_t ring, const void *Q, const void *K, con
 int fa_ring_plan(int rank, int world, int step, int n_local, int is_causal, int *src_rank, int *q_off,
                  int *q_rows, int *k_off, int *k_rows, int *block_causal);
 int fa_ring_local_rows(int rank, int world, int n_local, int is_causal, int64_t first_row[2], int rows[2]);
+
+/* ---- fa_mgpu_*: ONE process driving several GPUs of one box (the reference's
+ * harness is a single process, main.mm:881-1204).  The group owns a stream per device, its scratch
+ * memory and, for ring attention, the peer windows (plain peer access: no NCCL, no IPC).  Pointer
+ * arguments are arrays with one DEVICE pointer per group device, each on its own device.  Calls only
+ * enqueue work on the group's streams; fa_mgpu_synchronize waits for all devices. */
+typedef void *fa_mgpu_t;
+int fa_mgpu_create(fa_mgpu_t *group, const int *devices, int n_devices);
+int fa_mgpu_destroy(fa_mgpu_t group);
+int fa_mgpu_device_count(fa_mgpu_t group);
+fa_stream_t fa_mgpu_stream(fa_mgpu_t group, int index);   /* stream of the index-th device of the group */
+int fa_mgpu_synchronize(fa_mgpu_t group);
+/* batch x heads sharding (BASELINE config 4): device i runs heads[i] independent heads, its tensors are
+ * contiguous [heads[i], N, D]; no communication (kernels.metal:622). */
+int fa_mgpu_sharded_forward(fa_mgpu_t group, const void *const *Q, const void *const *K, const void *const *V,
+                            void *const *O, float *const *L, int N, int D, float scale, int is_causal,
+                            const int *heads, int dtype);
+int fa_mgpu_sharded_backward(fa_mgpu_t group, const void *const *Q, const void *const *K, const void *const *V,
+                             const void *const *O, const void *const *dO, const float *const *L, float *const *dQ,
+                             float *const *dK, float *const *dV, int N, int D, float scale, int is_causal,
+                             const int *heads, int dtype);
+/* ring / context-parallel attention (BASELINE config 5), layout as fa_ring_attention_*: device i is rank i */
+int fa_mgpu_ring_forward(fa_mgpu_t group, const void *const *Q, const void *const *K, const void *const *V,
+                         void *const *O, float *const *L, int n_local, int D, int H, float scale, int is_causal,
+                         int dtype);
+int fa_mgpu_ring_backward(fa_mgpu_t group, const void *const *Q, const void *const *K, const void *const *V,
+                          const void *const *O, const void *const *dO, const float *const *L, float *const *dQ,
+                          float *const *dK, float *const *dV, int n_local, int D, int H, float scale,
+                          int is_causal, int dtype);
 
 /* ---- host-buffer entry points ----------------------------------------------
  * The reference's buffers are MTLResourceStorageModeShared (main.mm:104-115):

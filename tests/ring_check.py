@@ -1,14 +1,19 @@
-"""Multi-GPU check + timing of ring attention (not a pytest file; run under torchrun):
+"""Multi-GPU check + timing of ring attention, one process per GPU (run under torchrun; wrapped by
+tests/test_gpu_ring_multi.py):
   python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 --master-port 29511 \
-      tests/ring_check.py [--n-total N] [--heads H] [--hdim D] [--causal 0|1] [--check 0|1] [--reps R]
+      tests/ring_check.py [--n-total N] [--heads H] [--hdim D] [--causal 0|1] [--check 0|1] [--reps R] [--bwd 0|1]
+                          [--transport auto|nccl|gather|peer]
 Every rank builds the same full Q/K/V (same seed), runs the single-GPU kernel on the full problem
-(when --check 1) and compares its ring output rows with it; then times the ring forward with CUDA
-events (max over ranks) and rank 0 prints one JSON line."""
+(when --check 1) and compares its ring output rows with it: the process EXITS NON-ZERO when a
+tolerance is exceeded (O 2e-2 max-abs, L 5e-3, gradients 1e-2 of the largest reference gradient).
+Then the ring is timed with CUDA events (max over ranks) and rank 0 prints one JSON line."""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 import flash_attention_metal_b200 as fa
+
+TOL_O, TOL_L, TOL_G = 2e-2, 5e-3, 1e-2
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--n-total", type=int, default=16384)
@@ -18,10 +23,8 @@ ap.add_argument("--causal", type=int, default=1)
 ap.add_argument("--check", type=int, default=1)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--bwd", type=int, default=0)
-ap.add_argument("--gather", type=int, default=0, help="1: all-gather forward mode (sets FA_RING_GATHER=1)")
+ap.add_argument("--transport", default="auto", choices=["auto", "nccl", "gather", "peer"])
 a = ap.parse_args()
-if a.gather:
-    os.environ["FA_RING_GATHER"] = "1"  # read by the library at its first ring forward
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -32,7 +35,8 @@ uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
 if rank == 0:
     uid = torch.frombuffer(bytearray(fa.ring_unique_id()), dtype=torch.uint8).cuda()
 dist.broadcast(uid, 0)
-ring = fa.Ring(bytes(uid.cpu().numpy().tobytes()), rank, world, local)
+transport = {"auto": fa.TRANSPORT_AUTO, "nccl": fa.TRANSPORT_NCCL, "gather": fa.TRANSPORT_NCCL_GATHER, "peer": fa.TRANSPORT_PEER}[a.transport]
+ring = fa.Ring(bytes(uid.cpu().numpy().tobytes()), rank, world, local, transport)
 rows = torch.cat([torch.arange(f, f + r) for f, r in fa.ring_local_rows(rank, world, n_local, bool(a.causal))]).cuda()
 g = torch.Generator(device="cuda").manual_seed(1)
 if a.check:
@@ -41,11 +45,12 @@ if a.check:
 else:
     Q, K, V = (torch.rand((H, n_local, D), device="cuda", generator=g).mul_(2).sub_(1).to(torch.bfloat16) for _ in range(3))
 O = torch.zeros_like(Q); L = torch.zeros((H, n_local), device="cuda")
-wsb = ring.workspace_bytes_gather(world, n_local, D, H, fa.BF16) if a.gather else ring.workspace_bytes(n_local, D, H, fa.BF16)
+wsb = ring.workspace_bytes(n_local, D, H, fa.BF16)
 ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
 st = torch.cuda.current_stream()
 run = lambda: ring.forward(Q, K, V, O, L, n_local, D, H, scale, a.causal, fa.BF16, ws, wsb, st)
 run(); torch.cuda.synchronize()
+failures = []
 err = errl = None
 if a.check:
     Of = torch.empty_like(Qf); Lf = torch.empty((H, N), device="cuda")
@@ -54,6 +59,12 @@ if a.check:
     err = (O.float() - Of[:, rows].float()).abs().max().item()
     errl = (L - Lf[:, rows]).abs().max().item()
     t = torch.tensor([err, errl], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); err, errl = t.tolist()
+    if not (err <= TOL_O): failures.append(f"O max-abs {err} > {TOL_O}")
+    if not (errl <= TOL_L): failures.append(f"L max-abs {errl} > {TOL_L}")
+    # a second call on the same ring must give the same bits (window / flag reuse across calls)
+    O1 = O.clone(); run(); torch.cuda.synchronize()
+    same = torch.tensor([float(torch.equal(O1, O))], device="cuda"); dist.all_reduce(same, op=dist.ReduceOp.MIN)
+    if same.item() != 1.0: failures.append("second forward call on the same ring differs bitwise from the first")
 berr = None
 if a.bwd:
     gd = torch.Generator(device="cuda").manual_seed(2)
@@ -73,6 +84,12 @@ if a.bwd:
         torch.cuda.synchronize()
         errs = [(x - y[:, rows]).abs().max().item() / y.abs().max().item() for x, y in ((dQ, gQ), (dK, gK), (dV, gV))]
         t = torch.tensor(errs, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); berr = t.tolist()
+        for name, x in zip(("dQ", "dK", "dV"), berr):
+            if not (x <= TOL_G): failures.append(f"{name} relative error {x} > {TOL_G}")
+        g1 = [x.clone() for x in (dQ, dK, dV)]; run_b(); torch.cuda.synchronize()
+        same = torch.tensor([float(all(torch.equal(x, y) for x, y in zip(g1, (dQ, dK, dV))))], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        if same.item() != 1.0: failures.append("second backward call differs bitwise from the first (not deterministic)")
     run_f = run
     run = lambda: (run_f(), run_b())
 for _ in range(2): run()
@@ -86,7 +103,10 @@ flops = 4.0 * H * N * N * D * (0.5 if a.causal else 1.0) * (3.5 if a.bwd else 1.
 if rank == 0:
     print(json.dumps({"ring_forward": True, "world": world, "N_total": N, "n_local": n_local, "H": H, "d": D, "causal": a.causal,
                       "ms": ms.item(), "tflops_total": flops / ms.item() / 1e9, "tflops_per_gpu": flops / ms.item() / 1e9 / world,
-                      "gather": a.gather, "max_abs_err_vs_single_gpu": err, "max_abs_L_err": errl, "bwd": a.bwd,
-                      "bwd_rel_err_dq_dk_dv_vs_single_gpu": berr}), flush=True)
+                      "transport": {1: "nccl", 2: "nccl_gather", 3: "peer"}[ring.transport], "max_abs_err_vs_single_gpu": err,
+                      "max_abs_L_err": errl, "bwd": a.bwd, "bwd_rel_err_dq_dk_dv_vs_single_gpu": berr, "failures": failures}), flush=True)
 ring.close()
 dist.destroy_process_group()
+if failures:
+    print(f"rank {rank}: RING CHECK FAILED: " + "; ".join(failures), file=sys.stderr, flush=True)
+    sys.exit(1)

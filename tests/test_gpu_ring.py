@@ -65,6 +65,57 @@ def test_rectangular_forward(fa, nq, nk, d):
         assert np.abs(L[h].cpu().numpy() - want_l).max() <= 5e-3
 
 
+@pytest.mark.parametrize("nq,d,cuts", [(300, 64, (0, 128, 1000)), (256, 128, (0, 520, 777, 1200)), (130, 128, (0, 64, 128, 192, 600))])
+def test_fused_merge_over_key_chunks(fa, nq, d, cuts):
+    """The ring's forward step on one GPU: the keys are processed in chunks, each launch folding its
+    partial into the running fp32 (O_acc, L_acc) in the kernel epilogue (first / middle / last); rows
+    below half_rows stop one chunk early (as the first zig-zag chunk does).  Equals attention over the
+    keys each row range has seen."""
+    import ctypes
+    import torch
+
+    fn = fa.lib().fa_debug_forward_partial
+    vp, i32 = ctypes.c_void_p, ctypes.c_int
+    fn.argtypes = [vp] * 7 + [i32, i32, i32, ctypes.c_float, i32, i32, i32, i32, i32, i32, vp]
+    H, scale, nk = 2, float(d ** -0.5), cuts[-1]
+    half = 96  # rows [0, half) see every chunk but the last one
+    qb, qf = bf16(oracle.init_random(H * nq * d, 41).reshape(H, nq, d))
+    kb, kf = bf16(oracle.init_random(H * nk * d, 42).reshape(H, nk, d))
+    vb, vf = bf16(oracle.init_random(H * nk * d, 43).reshape(H, nk, d))
+    Q = dev(qb.view(np.int16))
+    O = torch.zeros((H, nq, d), dtype=torch.int16, device="cuda")
+    L = torch.zeros((H, nq), device="cuda")
+    o_acc = torch.full((H, nq, d), float("nan"), device="cuda")
+    l_acc = torch.full((H, nq), float("nan"), device="cuda")
+    n_chunks = len(cuts) - 1
+    mode = lambda first, last: 0 if first and last else 1 if first else 3 if last else 2
+    for c in range(n_chunks):
+        k0, k1 = cuts[c], cuts[c + 1]
+        K = dev(np.ascontiguousarray(kb[:, k0:k1]).view(np.int16))
+        V = dev(np.ascontiguousarray(vb[:, k0:k1]).view(np.int16))
+        hi = mode(c == 0, c == n_chunks - 1)
+        if c < n_chunks - 1:   # both row ranges take part
+            lo = mode(c == 0, c == n_chunks - 2)
+            rc = fn(Q.data_ptr(), K.data_ptr(), V.data_ptr(), O.data_ptr(), L.data_ptr(), o_acc.data_ptr(), l_acc.data_ptr(),
+                    nq, k1 - k0, d, scale, H, 0, lo, hi, half, fa.BF16, None)
+        else:                  # last chunk: rows [half, nq) only -- every head at once needs the head stride of the full tensor,
+            rc = 0             # so go head by head with pointer offsets
+            for h in range(H):
+                off = (h * nq + half)
+                rc |= fn(Q.data_ptr() + off * d * 2, K.data_ptr() + h * (k1 - k0) * d * 2, V.data_ptr() + h * (k1 - k0) * d * 2,
+                         O.data_ptr() + off * d * 2, L.data_ptr() + off * 4, o_acc.data_ptr() + off * d * 4,
+                         l_acc.data_ptr() + off * 4, nq - half, k1 - k0, d, scale, 1, 0, hi, hi, 0, fa.BF16, None)
+        assert rc == 0, fa.lib().fa_last_error()
+    torch.cuda.synchronize()
+    got = oracle.from_half_bits(O.cpu().numpy().view(np.uint16), oracle.BF16)
+    for h in range(H):
+        want_lo, l_lo = rect_reference(qf[h][:half], kf[h][:cuts[-2]], vf[h][:cuts[-2]], scale)
+        want_hi, l_hi = rect_reference(qf[h][half:], kf[h], vf[h], scale)
+        assert np.abs(got[h][:half] - want_lo).max() <= TOL
+        assert np.abs(got[h][half:] - want_hi).max() <= TOL
+        assert np.abs(L[h].cpu().numpy() - np.concatenate([l_lo, l_hi])).max() <= 5e-3
+
+
 @pytest.mark.parametrize("causal", [False, True])
 @pytest.mark.parametrize("n,d", [(256, 64), (1000, 128)])
 def test_ring_world_one_matches_oracle(fa, causal, n, d):
@@ -158,36 +209,81 @@ def test_ring_backward_world_one_matches_oracle(fa, causal):
             assert err <= 2e-2 and err <= 1e-2 * np.abs(w).max()
 
 
+def rect_backward_reference(q, k, v, do, scale):
+    """fp64 dense gradients of non-causal attention with Nq != Nk (the formulas of kernels.metal:983-990,
+    1082-1089, 1160-1169 without the mask)."""
+    q, k, v, do = (x.astype(np.float64) for x in (q, k, v, do))
+    s = q @ k.T * scale
+    p = np.exp(s - s.max(1, keepdims=True))
+    p /= p.sum(1, keepdims=True)
+    o = p @ v
+    dv = p.T @ do
+    dp = do @ v.T
+    ds = p * (dp - (do * o).sum(1, keepdims=True)) * scale
+    return ds @ k, ds.T @ q, dv
+
+
+@pytest.mark.parametrize("nq,nk,d", [(200, 456, 64), (384, 130, 128), (1, 300, 64), (513, 64, 128)])
+def test_cross_attention_backward(fa, nq, nk, d):
+    """flash_attention_backward_rect: gradients of attention with Nq != Nk against a dense fp64 reference."""
+    import torch
+
+    H, scale = 2, float(d ** -0.5)
+    qb, qf = bf16(oracle.init_random(H * nq * d, 31).reshape(H, nq, d))
+    kb, kf = bf16(oracle.init_random(H * nk * d, 32).reshape(H, nk, d))
+    vb, vf = bf16(oracle.init_random(H * nk * d, 33).reshape(H, nk, d))
+    gb, gf = bf16(oracle.init_random(H * nq * d, 34).reshape(H, nq, d))
+    Q, K, V, dO = (dev(b.view(np.int16)) for b in (qb, kb, vb, gb))
+    O = torch.zeros((H, nq, d), dtype=torch.int16, device="cuda")
+    L = torch.zeros((H, nq), device="cuda")
+    fa.flash_attention_v4_half_rect(Q, K, V, O, nq, nk, d, scale, H * nq * d, nq * d, H * nk * d, nk * d, L, 1, H, fa.BF16)
+    delta = torch.zeros((H, nq), device="cuda")
+    fa.rowsum_delta(O, dO, delta, nq, d, H * nq * d, nq * d, 1, H, fa.BF16)
+    dQ = torch.full((H, nq, d), float("nan"), device="cuda")
+    dK, dV = (torch.full((H, nk, d), float("nan"), device="cuda") for _ in range(2))
+    fa.flash_attention_backward_rect(Q, K, V, dO, L, delta, dQ, dK, dV, nq, nk, d, scale, H * nq * d, nq * d, H * nk * d, nk * d,
+                                     False, 1, H, fa.BF16)
+    for h in range(H):
+        want = rect_backward_reference(qf[h], kf[h], vf[h], gf[h], scale)
+        for g, w in zip((dQ, dK, dV), want):
+            err = np.abs(g[h].cpu().numpy() - w).max()
+            assert err <= 2e-2 and err <= 1e-2 * np.abs(w).max()
+
+
 def test_rectangular_backward_blocks_sum_to_full_gradients(fa):
-    """The ring's building block: gradients of attention over two key chunks, each computed by the
-    rectangular backward from the full-row L and delta, add up to the gradients of the whole."""
+    """The ring's building block: the keys are cut into two ragged chunks; each chunk's rectangular
+    backward uses the L and delta of the FULL softmax rows; dQ accumulates over the chunks (acc_dq),
+    dK/dV of a chunk are complete after its own call.  Together they equal the gradients of the whole."""
     import torch
 
     n, d, scale = 512, 64, 0.125
-    ring = fa.Ring(fa.ring_unique_id(), 0, 1, 0)
-    ring.close()  # only here to make sure NCCL loading does not interfere; kernels are called directly
     bits, f = zip(*(bf16(oracle.init_random(n * d, s).reshape(n, d)) for s in (21, 22, 23, 24)))
     want = oracle.backward(*f, scale, False)
     Q, K, V, dO = (dev(b.view(np.int16)) for b in bits)
     O = torch.zeros((n, d), dtype=torch.int16, device="cuda")
     L = torch.zeros((n,), device="cuda")
     fa.flash_attention_v4_half(Q, K, V, O, n, d, scale, n * d, n * d, L, False, 1, 1, fa.BF16)
-    got = [torch.zeros((n, d), device="cuda") for _ in range(3)]
-    wsb = fa.workspace_bytes_backward(n, d, 1, 1)
-    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
-    fa.flash_attention_backward(Q, K, V, O, dO, L, *got, n, d, scale, n * d, n * d, False, 1, 1, fa.BF16, ws, wsb)
-    for g, w in zip(got, want):
+    delta = torch.zeros((n,), device="cuda")
+    fa.rowsum_delta(O, dO, delta, n, d, n * d, n * d, 1, 1, fa.BF16)
+    dQ, dK, dV = (torch.full((n, d), float("nan"), device="cuda") for _ in range(3))
+    cut = 200  # chunks of 200 and 312 keys: neither is a multiple of the 128-key tiles
+    for k0, k1, acc in ((0, cut, False), (cut, n, True)):
+        kp, vp = K.data_ptr() + k0 * d * 2, V.data_ptr() + k0 * d * 2
+        fa.flash_attention_backward_rect(Q, kp, vp, dO, L, delta, dQ, dK.data_ptr() + k0 * d * 4, dV.data_ptr() + k0 * d * 4,
+                                         n, k1 - k0, d, scale, n * d, n * d, (k1 - k0) * d, (k1 - k0) * d, acc, 1, 1, fa.BF16)
+    for g, w in zip((dQ, dK, dV), want):
         assert np.abs(g.cpu().numpy() - w).max() <= 1e-2 * np.abs(w).max()
 
 
-def test_cluster_of_eight():
+def test_cluster_of_eight(fa):
     """The key split also works with clusters of 8 CTAs (not the default: measured slower than 4)."""
-    import subprocess, sys, os
-    torch = pytest.importorskip("torch")
-    if not torch.cuda.is_available():
-        pytest.skip("no CUDA device")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, FA_FWD_SPLIT_MAX="8")
-    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_ring.py"), "-m", "gpu", "-q",
-                          "-k", "test_rectangular_forward"], env=env, capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-1000:]
+    import ctypes
+
+    setter = fa.lib().fa_debug_set_fwd_split_max
+    setter.argtypes = [ctypes.c_int]
+    setter(8)
+    try:
+        for nq, nk, d in [(200, 5000, 64), (130, 4500, 128), (700, 2100, 128)]:
+            test_rectangular_forward(fa, nq, nk, d)
+    finally:
+        setter(4)
