@@ -28,7 +28,7 @@ EXPORTS = (
     "naive_attention", "flash_attention", "flash_attention_v2", "flash_attention_v2_batched",
     "flash_attention_simd", "flash_attention_v4_half", "flash_attention_backward",
     "fa_workspace_bytes_backward", "fa_host_attention_f32", "fa_host_attention_half",
-    "fa_host_attention_fwd_bwd_half", "fa_host_release",
+    "fa_host_attention_fwd_bwd_half", "fa_host_attention_fwd_bwd_half_ex", "fa_host_release",
     "flash_attention_v4_half_rect", "fa_ring_unique_id_bytes", "fa_ring_get_unique_id", "fa_ring_create",
     "fa_ring_destroy", "fa_ring_workspace_bytes", "fa_ring_attention_forward", "fa_ring_plan", "fa_ring_local_rows",
     "fa_ring_workspace_bytes_backward", "fa_ring_attention_backward", "fa_ring_workspace_bytes_gather",
@@ -74,6 +74,7 @@ def lib() -> C.CDLL:
         L.fa_host_attention_f32.argtypes = [i32, vp, vp, vp, vp, i32, i32, f32, i32]
         L.fa_host_attention_half.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, i32, i32]
         L.fa_host_attention_fwd_bwd_half.argtypes = [vp] * 9 + [i32, i32, f32, i32, i32, i32, i32]
+        L.fa_host_attention_fwd_bwd_half_ex.argtypes = [vp] * 9 + [i32, i32, f32, i32, i32, i32, i32, i32]
         L.fa_host_release.restype = None
         L.fa_last_error.restype = C.c_char_p
         L.fa_launch_count.restype = C.c_long
@@ -323,6 +324,12 @@ def host_attention_half(Q, K, V, O, L_out, N, D, scale, is_causal, B, H, dtype):
 def host_attention_fwd_bwd_half(Q, K, V, dO, O, L_out, dQ, dK, dV, N, D, scale, is_causal, B, H, dtype):
     _check(lib().fa_host_attention_fwd_bwd_half(_ptr(Q), _ptr(K), _ptr(V), _ptr(dO), _ptr(O), _ptr(L_out), _ptr(dQ),
                                                 _ptr(dK), _ptr(dV), N, D, scale, int(is_causal), B, H, dtype))
+
+
+def host_attention_fwd_bwd_half_ex(Q, K, V, dO, O, L_out, dQ, dK, dV, N, D, scale, is_causal, B, H, dtype, grad_dtype=-1):
+    """grad_dtype -1: fp32 gradients (the reference's type); FP16 / BF16: gradients rounded on the device."""
+    _check(lib().fa_host_attention_fwd_bwd_half_ex(_ptr(Q), _ptr(K), _ptr(V), _ptr(dO), _ptr(O), _ptr(L_out), _ptr(dQ),
+                                                   _ptr(dK), _ptr(dV), N, D, scale, int(is_causal), B, H, dtype, grad_dtype))
 
 
 def host_release() -> None:

@@ -29,6 +29,8 @@ namespace fa { long long *g_trace_buffer = nullptr; }
 #endif
 
 namespace fa {
+static std::atomic<int> g_bwd_mode{0};
+int bwd_mode() { return g_bwd_mode.load(std::memory_order_relaxed); }
 static std::atomic<int> g_l2_group_mb{48};
 int l2_group_mb() { return g_l2_group_mb.load(std::memory_order_relaxed); }
 
@@ -71,6 +73,10 @@ int fa_debug_forward_partial(const void *Q, const void *K, const void *V, void *
   return launch_fwd_tc_rect(Q, K, V, O, L, Nq, Nk, D, scale, (int64_t)H * Nq * D, (int64_t)Nq * D, (int64_t)H * Nk * D,
                             (int64_t)Nk * D, is_causal, 1, H, dtype, (cudaStream_t)stream, &m);
 }
+
+// Development aid (not in the public header): 1 forces the two-kernel backward (bwd_tc.cu), 0 restores
+// the default (the fused kernel of bwd_fused.cu wherever it applies).  Tests run both.
+void fa_debug_set_bwd_mode(int mode) { g_bwd_mode.store(mode, std::memory_order_relaxed); }
 
 // Development aid (not in the public header): L2 budget of a dispatch group of heads, in MB.
 void fa_debug_set_l2_group_mb(int mb) { g_l2_group_mb.store(mb < 0 ? 0 : mb, std::memory_order_relaxed); }
@@ -154,8 +160,9 @@ int flash_attention_backward_rect(const void *Q, const void *K, const void *V, c
                                   int64_t kv_batch_stride, int64_t kv_head_stride, int acc_dq, int B, int H,
                                   int dtype, fa_stream_t stream) {
   FA_REQUIRE(dQ != nullptr || dK != nullptr, "nothing to compute: dQ, dK and dV are all null");
+  // no workspace in this call's signature: the two-kernel form (needs no ordering counters)
   return launch_bwd_tc_rect(Q, K, V, dO, L, delta, dQ, dK, dV, Nq, Nk, D, scale, q_batch_stride, q_head_stride,
-                            kv_batch_stride, kv_head_stride, 0, acc_dq, B, H, dtype, (cudaStream_t)stream);
+                            kv_batch_stride, kv_head_stride, 0, acc_dq, B, H, dtype, (cudaStream_t)stream, nullptr);
 }
 
 int fa_rowsum_delta(const void *O, const void *dO, float *delta, int N, int D, int64_t batch_stride,
@@ -171,9 +178,10 @@ int fa_rowsum_delta(const void *O, const void *dO, float *delta, int N, int D, i
 size_t fa_workspace_bytes_backward(int N, int D, int B, int H) {
   (void)D;
   if (N < 1 || B < 1 || H < 1) return 0;
-  // D_i = rowsum(dO o O): one float per (b, h, i), rounded up to 256 bytes
+  // ordering counters of the fused kernel (one per head and 128-row query tile), then
+  // D_i = rowsum(dO o O): one float per (b, h, i); both rounded up to 256 bytes
   size_t bytes = (size_t)B * H * N * sizeof(float);
-  return (bytes + 255) & ~(size_t)255;
+  return bwd_fused_sem_bytes(N, B, H) + ((bytes + 255) & ~(size_t)255);
 }
 
 }  // extern "C"

@@ -829,7 +829,7 @@ int launch_bwd_tc_rect(const void *Q, const void *K, const void *V, const void *
                        const float *delta, float *dQ, float *dK, float *dV, int Nq, int Nk, int D, float scale,
                        int64_t q_batch_stride, int64_t q_head_stride, int64_t kv_batch_stride,
                        int64_t kv_head_stride, int is_causal, int acc_dq, int B, int H, int dtype,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, void *fused_sems) {
   FA_REQUIRE(Q && K && V && dO && L && delta, "null tensor pointer");
   FA_REQUIRE((dK == nullptr) == (dV == nullptr), "dK and dV go together");
   FA_REQUIRE(Nq >= 1 && Nk >= 1, "N must be >= 1 (got %d x %d)", Nq, Nk);
@@ -846,6 +846,12 @@ int launch_bwd_tc_rect(const void *Q, const void *K, const void *V, const void *
   FA_REQUIRE((H == 1 || (q_head_stride >= (int64_t)Nq * D && kv_head_stride >= (int64_t)Nk * D)) &&
                  (B == 1 || (q_batch_stride >= (int64_t)Nq * D && kv_batch_stride >= (int64_t)Nk * D)),
              "heads overlap: stride smaller than N*D");
+  // One fused kernel (five GEMMs per tile pair, dQ by ordered TMA add-reduction, bwd_fused.cu) when all
+  // three gradients are wanted and the caller provided the ordering counters; otherwise the two-kernel
+  // form below (seven GEMMs, every gradient tile owned by one CTA).
+  if (fused_sems != nullptr && dQ != nullptr && dK != nullptr && bwd_mode() != 1)
+    return launch_bwd_fused(Q, K, V, dO, L, delta, dQ, dK, dV, Nq, Nk, D, scale, q_batch_stride, q_head_stride,
+                            kv_batch_stride, kv_head_stride, is_causal, acc_dq, B, H, dtype, fused_sems, stream);
   const CUtensorMap *maps[4];
   int rc;
   if ((rc = tensor_map_bhnd(&maps[0], Q, dtype, Nq, D, H, B, q_head_stride, q_batch_stride, 128)) != FA_OK) return rc;
@@ -883,19 +889,22 @@ int launch_bwd_tc(const void *Q, const void *K, const void *V, const void *O, co
   FA_REQUIRE(B >= 1 && H >= 1 && H <= 65535 && B <= 65535, "bad B/H (%d, %d)", B, H);
   FA_REQUIRE(aligned16(O), "tensors must be 16-byte aligned");
   FA_REQUIRE(batch_stride % D == 0 && head_stride % D == 0, "strides must be multiples of D");
-  // delta is indexed like L: offset / D + row; its extent follows the strides
+  // workspace = [ordering counters of the fused kernel | delta]; delta is indexed like L: offset / D + row,
+  // so its extent follows the strides
   const size_t need = fa_workspace_bytes_backward(N, D, B, H);
+  const size_t sem_bytes = bwd_fused_sem_bytes(N, B, H);
   const int64_t last = ((int64_t)(B - 1) * batch_stride + (int64_t)(H - 1) * head_stride) / D + N;
-  if (workspace == nullptr || workspace_bytes < need || (size_t)last * sizeof(float) > workspace_bytes)
+  if (workspace == nullptr || workspace_bytes < need || sem_bytes + (size_t)last * sizeof(float) > workspace_bytes)
     return set_error(FA_ERR_WORKSPACE,
                      "backward workspace too small: need %zu bytes (fa_workspace_bytes_backward; contiguous "
                      "[B,H,N,D] layout assumed), got %zu",
                      need, workspace_bytes);
-  float *delta = reinterpret_cast<float *>(workspace);
+  FA_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15u) == 0, "workspace must be 16-byte aligned");
+  float *delta = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + sem_bytes);
   int rc = launch_bwd_delta(O, dO, delta, N, D, batch_stride, head_stride, B, H, dtype, stream);
   if (rc != FA_OK) return rc;
   return launch_bwd_tc_rect(Q, K, V, dO, L, delta, dQ, dK, dV, N, N, D, scale, batch_stride, head_stride, batch_stride,
-                            head_stride, is_causal, 0, B, H, dtype, stream);
+                            head_stride, is_causal, 0, B, H, dtype, stream, workspace);
 }
 
 }  // namespace fa

@@ -99,6 +99,15 @@ int launch_bwd_tc_rect(const void *Q, const void *K, const void *V, const void *
                        const float *delta, float *dQ, float *dK, float *dV, int Nq, int Nk, int D, float scale,
                        int64_t q_batch_stride, int64_t q_head_stride, int64_t kv_batch_stride,
                        int64_t kv_head_stride, int is_causal, int acc_dq, int B, int H, int dtype,
-                       cudaStream_t stream);
+                       cudaStream_t stream, void *fused_sems = nullptr);
+
+// fused five-GEMM backward (bwd_fused.cu): `sems` = bwd_fused_sem_bytes() bytes of ordering counters
+size_t bwd_fused_sem_bytes(int Nq, int B, int H);
+int launch_bwd_fused(const void *Q, const void *K, const void *V, const void *dO, const float *L, const float *delta,
+                     float *dQ, float *dK, float *dV, int Nq, int Nk, int D, float scale, int64_t q_batch_stride,
+                     int64_t q_head_stride, int64_t kv_batch_stride, int64_t kv_head_stride, int is_causal, int acc_dq,
+                     int B, int H, int dtype, void *sems, cudaStream_t stream);
+// 0 auto (fused when possible), 1 always the two-kernel form, 2 as 0 (reserved); fa_debug_set_bwd_mode
+int bwd_mode();
 
 }  // namespace fa

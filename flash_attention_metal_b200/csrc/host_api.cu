@@ -17,7 +17,7 @@ namespace fa {
 namespace {
 
 struct HostPool {
-  static constexpr int kSlots = 12;
+  static constexpr int kSlots = 13;
   void *ptr[kSlots] = {};
   size_t cap[kSlots] = {};
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
@@ -71,10 +71,28 @@ struct HostPool {
 
 HostPool g_pool;
 
+// fp32 -> 16-bit (round to nearest even), 8 elements per thread: the optional 16-bit gradient output of
+// the host-buffer call (halves the device->host bytes, which bound that call)
+template <int IS_BF16>
+__global__ void __launch_bounds__(256) narrow_kernel(const float *__restrict__ src, uint16_t *__restrict__ dst, size_t n8) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = reinterpret_cast<const float4 *>(src)[2 * i], b = reinterpret_cast<const float4 *>(src)[2 * i + 1];
+  uint32_t w[4];
+  const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (IS_BF16) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[k]) : "f"(v[2 * k + 1]), "f"(v[2 * k]));
+    else asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(w[k]) : "f"(v[2 * k + 1]), "f"(v[2 * k]));
+  }
+  reinterpret_cast<uint4 *>(dst)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 int host_half_impl(const void *Q, const void *K, const void *V, const void *dO, void *O, float *L,
-                   float *dQ, float *dK, float *dV, int N, int D, float scale, int is_causal, int B,
-                   int H, int dtype) {
+                   void *dQ, void *dK, void *dV, int N, int D, float scale, int is_causal, int B,
+                   int H, int dtype, int grad_dtype = -1) {
   const bool bwd = dO != nullptr;
+  const bool narrow = grad_dtype >= 0;  // gradients leave the device as 16-bit values
   FA_REQUIRE(Q && K && V && O && N >= 1 && B >= 1 && H >= 1, "bad arguments");
   FA_REQUIRE(D == 64 || D == 128, "D must be 64 or 128 (got %d)", D);
   FA_REQUIRE(!bwd || (dQ && dK && dV), "backward needs dQ, dK and dV");
@@ -96,6 +114,10 @@ int host_half_impl(const void *Q, const void *K, const void *V, const void *dO, 
         (rc = g_pool.get(9, fa_workspace_bytes_backward(N, D, 1, heads) + 256, &dDelta)))
       return rc;
   }
+  void *nQ = nullptr, *nK = nullptr, *nV = nullptr;
+  if (bwd && narrow &&
+      ((rc = g_pool.get(10, heads * hb, &nQ)) || (rc = g_pool.get(11, heads * hb, &nK)) || (rc = g_pool.get(12, heads * hb, &nV))))
+    return rc;
   // Groups of heads.  Steady state: enough CTAs per group to fill the GPU, enough groups to overlap
   // copies.  The device->host direction carries the most bytes (fp32 gradients), so the pipeline is
   // bound by how early the first result copy can start: the first groups are small (1, 1, 2 heads)
@@ -137,15 +159,32 @@ int host_half_impl(const void *Q, const void *K, const void *V, const void *dO, 
     if (bwd) {
       rc = launch_bwd_tc(atw(dq_, ob), atw(dk_, ob), atw(dv_, ob), atw(dOut, ob), atw(do_, ob), (float *)atw(dL, ol),
                          (float *)atw(gQ, of), (float *)atw(gK, of), (float *)atw(gV, of), N, D, scale,
-                         (int64_t)nh * head_elems, (int64_t)head_elems, is_causal, 1, nh, dtype, atw(dDelta, ol),
-                         fa_workspace_bytes_backward(N, D, 1, nh), g_pool.s_run);
+                         (int64_t)nh * head_elems, (int64_t)head_elems, is_causal, 1, nh, dtype, dDelta,
+                         fa_workspace_bytes_backward(N, D, 1, nh), g_pool.s_run);  // one scratch: the groups run in order
       if (rc != FA_OK) return rc;
+      if (narrow) {
+        const size_t n8 = (size_t)nh * head_elems / 8;
+        const unsigned blocks = (unsigned)((n8 + 255) / 256);
+        void *src[3] = {gQ, gK, gV}, *dst[3] = {nQ, nK, nV};
+        for (int t = 0; t < 3; ++t) {
+          if (grad_dtype == FA_DTYPE_BF16)
+            narrow_kernel<1><<<blocks, 256, 0, g_pool.s_run>>>((const float *)atw(src[t], of), (uint16_t *)atw(dst[t], ob), n8);
+          else
+            narrow_kernel<0><<<blocks, 256, 0, g_pool.s_run>>>((const float *)atw(src[t], of), (uint16_t *)atw(dst[t], ob), n8);
+        }
+        FA_CUDA_CHECK(cudaGetLastError());
+        count_launch(3);
+      }
     }
     FA_CUDA_CHECK(cudaEventRecord(g_pool.run_done[g], g_pool.s_run));
     FA_CUDA_CHECK(cudaStreamWaitEvent(g_pool.s_out, g_pool.run_done[g], 0));
     FA_CUDA_CHECK(cudaMemcpyAsync(atw(O, ob), at(dOut, ob), nh * hb, cudaMemcpyDeviceToHost, g_pool.s_out));
     if (L) FA_CUDA_CHECK(cudaMemcpyAsync(atw(L, ol), at(dL, ol), nh * hl, cudaMemcpyDeviceToHost, g_pool.s_out));
-    if (bwd) {
+    if (bwd && narrow) {
+      FA_CUDA_CHECK(cudaMemcpyAsync(atw(dQ, ob), at(nQ, ob), nh * hb, cudaMemcpyDeviceToHost, g_pool.s_out));
+      FA_CUDA_CHECK(cudaMemcpyAsync(atw(dK, ob), at(nK, ob), nh * hb, cudaMemcpyDeviceToHost, g_pool.s_out));
+      FA_CUDA_CHECK(cudaMemcpyAsync(atw(dV, ob), at(nV, ob), nh * hb, cudaMemcpyDeviceToHost, g_pool.s_out));
+    } else if (bwd) {
       FA_CUDA_CHECK(cudaMemcpyAsync(atw(dQ, of), at(gQ, of), nh * hf, cudaMemcpyDeviceToHost, g_pool.s_out));
       FA_CUDA_CHECK(cudaMemcpyAsync(atw(dK, of), at(gK, of), nh * hf, cudaMemcpyDeviceToHost, g_pool.s_out));
       FA_CUDA_CHECK(cudaMemcpyAsync(atw(dV, of), at(gV, of), nh * hf, cudaMemcpyDeviceToHost, g_pool.s_out));
@@ -197,6 +236,16 @@ int fa_host_attention_fwd_bwd_half(const void *Q, const void *K, const void *V, 
                                    int is_causal, int B, int H, int dtype) {
   FA_REQUIRE(dO != nullptr, "dO is null");
   return host_half_impl(Q, K, V, dO, O, L_out, dQ, dK, dV, N, D, scale, is_causal, B, H, dtype);
+}
+
+int fa_host_attention_fwd_bwd_half_ex(const void *Q, const void *K, const void *V, const void *dO, void *O,
+                                      float *L_out, void *dQ, void *dK, void *dV, int N, int D, float scale,
+                                      int is_causal, int B, int H, int dtype, int grad_dtype) {
+  FA_REQUIRE(dO != nullptr, "dO is null");
+  FA_REQUIRE(grad_dtype == -1 || grad_dtype == FA_DTYPE_FP16 || grad_dtype == FA_DTYPE_BF16,
+             "grad_dtype must be -1 (fp32), FA_DTYPE_FP16 or FA_DTYPE_BF16");
+  FA_REQUIRE(grad_dtype < 0 || ((size_t)N * D) % 8 == 0, "16-bit gradients need N * D to be a multiple of 8");
+  return host_half_impl(Q, K, V, dO, O, L_out, dQ, dK, dV, N, D, scale, is_causal, B, H, dtype, grad_dtype);
 }
 
 void fa_host_release(void) {

@@ -10,7 +10,7 @@
 //     PEER transport -- copy-engine pulls over NVLink, flags driven by stream memory operations.
 #include <cuda_runtime.h>
 
-#include <vector>
+#include <algorithm>
 
 #include "fa_internal.h"
 #include "ring.h"
@@ -51,16 +51,30 @@ int mgpu_grow_windows(MgpuGroup *g, size_t bytes) {
 
 namespace {
 
-int group_scratch(MgpuGroup *g, int i, size_t bytes, void **out) {
-  if (g->ws_cap[i] < bytes) {
-    FA_CUDA_CHECK(cudaStreamSynchronize(g->streams[i]));
-    if (g->ws[i]) cudaFree(g->ws[i]);
-    g->ws[i] = nullptr;
-    g->ws_cap[i] = 0;
-    FA_CUDA_CHECK(cudaMalloc(&g->ws[i], bytes));
-    g->ws_cap[i] = bytes;
+// Make every device's scratch at least `bytes` and every rank's peer window at least `window_bytes`
+// BEFORE anything of the call is enqueued.  Growing means freeing, and cudaFree / cudaDeviceSynchronize
+// wait for the whole device: once one rank's ring work is in its streams (blocked on flags that a later
+// rank has yet to write) such a wait would never return.  At the start of a call every earlier call has
+// been enqueued for all ranks, so the wait is safe there -- and only there.
+int group_reserve(MgpuGroup *g, size_t bytes, size_t window_bytes) {
+  bool grow = false;
+  for (int i = 0; i < g->n; ++i) grow = grow || g->ws_cap[i] < bytes;
+  if (grow) {
+    for (int i = 0; i < g->n; ++i) {
+      FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
+      FA_CUDA_CHECK(cudaDeviceSynchronize());
+    }
+    for (int i = 0; i < g->n; ++i) {
+      if (g->ws_cap[i] >= bytes) continue;
+      FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
+      if (g->ws[i]) cudaFree(g->ws[i]);
+      g->ws[i] = nullptr;
+      g->ws_cap[i] = 0;
+      FA_CUDA_CHECK(cudaMalloc(&g->ws[i], bytes));
+      g->ws_cap[i] = bytes;
+    }
   }
-  *out = g->ws[i];
+  if (window_bytes > 0 && g->rings[0]->data_cap < window_bytes) return mgpu_grow_windows(g, window_bytes);
   return FA_OK;
 }
 
@@ -179,16 +193,18 @@ int fa_mgpu_sharded_backward(void *group, const void *const *Q, const void *cons
                              const int *heads, int dtype) {
   MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
   FA_REQUIRE(g && Q && K && V && O && dO && L && dQ && dK && dV && heads, "null argument");
+  size_t need = 0;
+  for (int i = 0; i < g->n; ++i)
+    if (heads[i] > 0) need = std::max(need, fa_workspace_bytes_backward(N, D, 1, heads[i]));
+  int rc = group_reserve(g, need, 0);
+  if (rc != FA_OK) return rc;
   for (int i = 0; i < g->n; ++i) {
     if (heads[i] <= 0) continue;
     FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
     const int64_t hs = (int64_t)N * D;
     const size_t wsb = fa_workspace_bytes_backward(N, D, 1, heads[i]);
-    void *ws = nullptr;
-    int rc = group_scratch(g, i, wsb, &ws);
-    if (rc != FA_OK) return rc;
     rc = launch_bwd_tc(Q[i], K[i], V[i], O[i], dO[i], L[i], dQ[i], dK[i], dV[i], N, D, scale, hs * heads[i], hs, is_causal, 1,
-                       heads[i], dtype, ws, wsb, g->streams[i]);
+                       heads[i], dtype, g->ws[i], wsb, g->streams[i]);
     if (rc != FA_OK) return rc;
   }
   return FA_OK;
@@ -200,13 +216,13 @@ int fa_mgpu_ring_forward(void *group, const void *const *Q, const void *const *K
   FA_REQUIRE(g && Q && K && V && O, "null argument");
   const size_t wsb = fa_ring_workspace_bytes_ex(g->n, FA_RING_TRANSPORT_PEER, n_local, D, H, dtype);
   FA_REQUIRE(wsb > 0, "bad shape");
+  const size_t tile_bytes = (size_t)H * n_local * D * 2;
+  int rc = group_reserve(g, wsb, g->n > 1 ? 2 * tile_bytes : 0);  // window: [K | V]
+  if (rc != FA_OK) return rc;
   for (int i = 0; i < g->n; ++i) {
     FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
-    void *ws = nullptr;
-    int rc = group_scratch(g, i, wsb, &ws);
-    if (rc != FA_OK) return rc;
     rc = fa_ring_attention_forward(g->rings[i], Q[i], K[i], V[i], O[i], L ? L[i] : nullptr, n_local, D, H, scale, is_causal,
-                                   dtype, ws, wsb, g->streams[i]);
+                                   dtype, g->ws[i], wsb, g->streams[i]);
     if (rc != FA_OK) return rc;
   }
   return FA_OK;
@@ -220,13 +236,13 @@ int fa_mgpu_ring_backward(void *group, const void *const *Q, const void *const *
   FA_REQUIRE(g && Q && K && V && O && dO && L && dQ && dK && dV, "null argument");
   const size_t wsb = fa_ring_workspace_bytes_backward(n_local, D, H, dtype);
   FA_REQUIRE(wsb > 0, "bad shape");
+  const size_t tile_elems = (size_t)H * n_local * D;
+  int rc = group_reserve(g, wsb, g->n > 1 ? 2 * tile_elems * 2 + 4 * tile_elems * 4 : 0);  // window: [K | V][2 x (dK | dV)]
+  if (rc != FA_OK) return rc;
   for (int i = 0; i < g->n; ++i) {
     FA_CUDA_CHECK(cudaSetDevice(g->devices[i]));
-    void *ws = nullptr;
-    int rc = group_scratch(g, i, wsb, &ws);
-    if (rc != FA_OK) return rc;
     rc = fa_ring_attention_backward(g->rings[i], Q[i], K[i], V[i], O[i], dO[i], L[i], dQ[i], dK[i], dV[i], n_local, D, H, scale,
-                                    is_causal, dtype, ws, wsb, g->streams[i]);
+                                    is_causal, dtype, g->ws[i], wsb, g->streams[i]);
     if (rc != FA_OK) return rc;
   }
   return FA_OK;

@@ -661,7 +661,8 @@ size_t fa_ring_workspace_bytes_backward(int n_local, int D, int H, int dtype) {
                  + 2 * tile * 4            // this step's dK|dV block (fp32)
                  + 2 * (2 * tile * 4)      // two outgoing dK|dV accumulators (NCCL transport)
                  + 2 * tile * 4            // incoming dK|dV accumulator
-                 + (size_t)H * n_local * 4;  // delta
+                 + (size_t)H * n_local * 4   // delta
+                 + 256 + bwd_fused_sem_bytes(n_local, 1, H);  // ordering counters of the fused backward kernel
   return bytes + 1024;
 }
 
@@ -696,6 +697,7 @@ int fa_ring_attention_backward(void *ring, const void *Q, const void *K, const v
   float *acc_out[2] = {tmp + 2 * tile_elems, tmp + 4 * tile_elems};
   float *acc_in = tmp + 6 * tile_elems;
   float *delta = tmp + 8 * tile_elems;
+  void *sems = reinterpret_cast<void *>((reinterpret_cast<uintptr_t>(delta + (size_t)H * n_local) + 255) & ~(uintptr_t)255);
   const int next = (r->rank + 1) % P, prev = (r->rank - 1 + P) % P;
   const int64_t hs = (int64_t)n_local * D;
   int rc = launch_bwd_delta(O, dO, delta, n_local, D, (int64_t)H * hs, hs, 1, H, dtype, st);
@@ -712,7 +714,7 @@ int fa_ring_attention_backward(void *ring, const void *Q, const void *K, const v
     float *blk_dk = (P == 1 ? dK : tmp) + (int64_t)b.k_off * D;
     float *blk_dv = (P == 1 ? dV : tmp + tile_elems) + (int64_t)b.k_off * D;
     return launch_bwd_tc_rect(q, k, v, g, L + b.q_off, delta + b.q_off, dQ + (int64_t)b.q_off * D, blk_dk, blk_dv, b.q_rows,
-                              b.k_rows, D, scale, (int64_t)H * hs, hs, (int64_t)H * hs, hs, b.causal, s > 0, 1, H, dtype, st);
+                              b.k_rows, D, scale, (int64_t)H * hs, hs, (int64_t)H * hs, hs, b.causal, s > 0, 1, H, dtype, st, sems);
   };
   auto add_block = [&](float *out, const Block &b, bool has_in) -> int {
     const int64_t vecs = (int64_t)tile_elems / 4;

@@ -52,11 +52,32 @@ inline int make_tensor_map_bhnd(CUtensorMap *map, const void *base, int dtype, i
   return FA_OK;
 }
 
+// Row-major [B, H, N, D] fp32 tensor (dQ), box = 32 floats (128 bytes) x 128 rows, 128-byte swizzle: the
+// staging layout of the fused backward's dQ reduction (TMA store / add-reduction from shared memory).
+inline int make_tensor_map_f32_bhnd(CUtensorMap *map, const void *base, int N, int D, int H, int B, int64_t head_stride,
+                                    int64_t batch_stride) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return set_error(FA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t hs = (cuuint64_t)(H > 1 ? head_stride : (int64_t)N * D) * 4;
+  cuuint64_t bs = (cuuint64_t)(B > 1 ? batch_stride : (int64_t)H * N * D) * 4;
+  cuuint64_t strides[3] = {(cuuint64_t)D * 4, hs, bs};
+  cuuint32_t box[4] = {32u, 128u, 1u, 1u};
+  cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(FA_ERR_CUDA, "cuTensorMapEncodeTiled (fp32) failed (CUresult %d; N=%d D=%d H=%d B=%d)", (int)r, N, D, H, B);
+  return FA_OK;
+}
+
 // Cached form: the harness' small-N launches are latency-bound and three to four driver encodes per
 // call cost more than the launch itself.  A tensor map depends only on (address, shape, strides, box),
 // never on memory contents, so the encoded 128 bytes can be reused for as long as the key matches.
 // Per-thread cache (no locking), 32 entries, round-robin replacement; the returned pointer stays
 // valid until 32 further misses on this thread, i.e. well past the launch that copies it by value.
+constexpr int kTensorMapF32 = 2;  // pseudo dtype of tensor_map_bhnd: the fp32 dQ map above (box_rows ignored)
 inline int tensor_map_bhnd(const CUtensorMap **out, const void *base, int dtype, int N, int D, int H, int B,
                            int64_t head_stride, int64_t batch_stride, int box_rows) {
   struct Entry {
@@ -79,7 +100,8 @@ inline int tensor_map_bhnd(const CUtensorMap **out, const void *base, int dtype,
   }
   Entry &e = cache[next];
   e.valid = 0;
-  const int rc = make_tensor_map_bhnd(&e.map, base, dtype, N, D, H, B, head_stride, batch_stride, box_rows);
+  const int rc = dtype == kTensorMapF32 ? make_tensor_map_f32_bhnd(&e.map, base, N, D, H, B, head_stride, batch_stride)
+                                        : make_tensor_map_bhnd(&e.map, base, dtype, N, D, H, B, head_stride, batch_stride, box_rows);
   if (rc != FA_OK) return rc;
   e.base = base; e.hs = hs; e.bs = bs; e.dtype = dtype; e.N = N; e.D = D; e.H = H; e.B = B; e.box_rows = box_rows;
   e.valid = 1;

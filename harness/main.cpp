@@ -205,7 +205,12 @@ struct Dev {
   void zero() { CUDA_OK(cudaMemset(p, 0, n * sizeof(T))); }
 };
 
+int run_presets(int config, int gpus, double peak_tflops, int reps, long long max_n);  // presets.cpp
+
 struct Opts {
+  int config = 0;      // 0: the reference harness' four phases; 1..5: BASELINE.json configurations (--config)
+  int gpus = 1;        // --gpus N (configs 4 and 5)
+  int phases = 0xf;    // bit i: run phase i+1
   int reps = 10, warmup = 3;
   int dtype = FA_DTYPE_FP16;  // the reference's half type; --dtype bf16 for the B200 flagship type
   bool causal = false;
@@ -262,6 +267,8 @@ static std::vector<float> from_half(const std::vector<uint16_t> &h, int dtype) {
   return x;
 }
 
+static int run_harness(const Opts &opt);
+
 int main(int argc, char **argv) {
   Opts opt;
   for (int i = 1; i < argc; ++i) {
@@ -274,11 +281,55 @@ int main(int argc, char **argv) {
     else if (a == "--max-n") opt.maxN = atoi(next().c_str());
     else if (a == "--reps") opt.reps = atoi(next().c_str());
     else if (a == "--csv") opt.csv = next();
+    else if (a == "--config") opt.config = atoi(next().c_str());
+    else if (a == "--gpus") opt.gpus = atoi(next().c_str());
+    else if (a == "--peak-tflops") opt.peak_tflops = atof(next().c_str());
     else if (a == "--help") {
-      std::cout << "flash_attn [--dtype fp16|bf16] [--causal] [--d 64|128] [--max-n N] [--reps R] [--quick] [--csv FILE]\n";
+      std::cout << "flash_attn [--dtype fp16|bf16] [--causal] [--d 64|128] [--max-n N] [--reps R] [--quick] [--csv FILE]\n"
+                   "           [--config 1..5 [--gpus N]] [--peak-tflops T]\n"
+                   "  --config 1  CPU reference verifier alone, N=128 fp32 (main.mm:128-159 loop order)\n"
+                   "  --config 2  the sweep N=128..16384 for fp16 and bf16, causal and not: four CSVs\n"
+                   "  --config 3  causal bf16 fwd+bwd, B=1 H=16 N=16384 d=128, one GPU\n"
+                   "  --config 4  B=8 H=12 N=4096 d=64 causal bf16, 96 heads split over 1/2/4/8 GPUs (--gpus)\n"
+                   "  --config 5  one causal sequence N=131072..1M (--max-n), d=128, ring attention over --gpus GPUs\n";
       return 0;
     }
   }
+  if (opt.config == 1) {
+    // BASELINE config 1: the reference's CPU verifier, exact loop order, single thread, N=128, d=64, fp32
+    const int n1 = 128, D1 = 64;
+    std::vector<float> q((size_t)n1 * D1), o1(q.size());
+    initRandom(q.data(), q.size());
+    auto t1 = std::chrono::steady_clock::now();
+    cpu_forward_faithful(q.data(), q.data(), q.data(), o1.data(), n1, D1, 1.0f / std::sqrt((float)D1));
+    double ms1 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
+    double sum = 0;
+    for (float x : o1) sum += x;
+    std::cout << "config 1: CPU reference (faithful loop order, 1 thread) N=128 d=64 fp32 non-causal: " << ms1 << " ms, "
+              << 4.0 * n1 * n1 * D1 / (ms1 * 1e6) << " GFLOP/s; O[0] = " << o1[0] << ", sum(O) = " << sum << std::endl;
+    return 0;
+  }
+  if (opt.config == 2) {
+    int rc = 0;
+    for (int dt : {FA_DTYPE_FP16, FA_DTYPE_BF16})
+      for (int causal = 0; causal < 2; ++causal) {
+        Opts o = opt;
+        o.dtype = dt;
+        o.causal = causal != 0;
+        o.phases = (dt == FA_DTYPE_FP16 && !causal) ? 0x7 : 0x4;  // verification phases once, then sweeps only
+        o.csv = std::string("benchmark_results_") + (dt == FA_DTYPE_BF16 ? "bf16" : "fp16") + (causal ? "_causal" : "") + ".csv";
+        std::cout << "\n=== config 2: sweep, half type " << (dt == FA_DTYPE_BF16 ? "bf16" : "fp16") << (causal ? ", causal" : ", non-causal")
+                  << " -> " << o.csv << " ===" << std::endl;
+        rc |= run_harness(o);
+      }
+    return rc;
+  }
+  if (opt.config >= 3 && opt.config <= 5)
+    return run_presets(opt.config, opt.gpus, opt.peak_tflops, opt.reps, opt.maxN > 16384 ? (long long)opt.maxN : 1048576ll) ? 2 : 0;
+  return run_harness(opt);
+}
+
+static int run_harness(const Opts &opt) {
   const int D = opt.D;
   const float SCALE = 1.0f / std::sqrt((float)D);
   const char *tname = opt.dtype == FA_DTYPE_BF16 ? "bf16" : "fp16";
@@ -290,7 +341,7 @@ int main(int argc, char **argv) {
             << ", host threads " << host_threads() << " of " << std::thread::hardware_concurrency() << std::endl;
 
   // ------------------------------------------------------------------ phase 1 --
-  {
+  if (opt.phases & 1) {
     const int N = opt.quick ? 256 : 1024;
     std::vector<float> q((size_t)N * D), k(q.size()), v(q.size()), O_cpu(q.size());
     initRandom(q.data(), q.size());
@@ -355,7 +406,7 @@ int main(int argc, char **argv) {
   }
 
   // ------------------------------------------------------------------ phase 2 --
-  {
+  if (opt.phases & 2) {
     std::cout << "Verifying Causal Masking..." << std::endl;
     const int Nc = 128;
     std::vector<float> q((size_t)Nc * D), O_ref(q.size());
@@ -381,6 +432,8 @@ int main(int argc, char **argv) {
   }
 
   // ------------------------------------------------------------------ phase 3 --
+  std::vector<int> sizes = {128, 256, 512, 1024, 2048, 4096, 8192, 16384};
+  if (opt.phases & 4) {
   std::cout << "\n--- Benchmarking ---\n";
   const char *header =
       "N,Naive(ms),Flash(ms),FlashV2(ms),FlashV3(ms),FlashV4(ms),SpeedupV1,SpeedupV2,SpeedupV3,SpeedupV4,"
@@ -388,7 +441,6 @@ int main(int argc, char **argv) {
   std::cout << header << std::endl;
   std::ofstream csv(opt.csv);
   if (csv.is_open()) csv << header << "\n";
-  std::vector<int> sizes = {128, 256, 512, 1024, 2048, 4096, 8192, 16384};
   const int ic = opt.causal ? 1 : 0;
   for (int n : sizes) {
     if (n > opt.maxN) break;
@@ -430,8 +482,10 @@ int main(int argc, char **argv) {
     if (csv.is_open()) { csv << line << "\n"; csv.flush(); }
   }
   if (csv.is_open()) csv.close();
+  }
 
   // ------------------------------------------------------------------ phase 4 --
+  if (opt.phases & 8) {
   std::cout << "\n--- High Occupancy Benchmark (B=16, H=8) ---\n";
   std::cout << "N,FlashV2(ms),FlashV4(ms),Backward(ms),SpeedupV4vsV2,V4_TFLOPs,Bwd_TFLOPs" << std::endl;
   const int B = 16, H = 8;
@@ -494,6 +548,7 @@ int main(int argc, char **argv) {
     snprintf(line, sizeof(line), "%d,%g,%g,%g,%g,%.3f,%.3f,%s", n, tv2, tv4, tb, tv2 / tv4, flop / (tv4 * 1e9),
              tb > 0 ? 2.5 * flop / (tb * 1e9) : 0.0, status.c_str());
     std::cout << line << std::endl;
+  }
   }
   if (g_failures) std::cout << g_failures << " check(s) FAILED" << std::endl;
   return g_failures ? 2 : 0;

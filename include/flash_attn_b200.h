@@ -240,6 +240,13 @@ int fa_host_attention_half(const void *Q, const void *K, const void *V, void *O,
 int fa_host_attention_fwd_bwd_half(const void *Q, const void *K, const void *V, const void *dO,
                                    void *O, float *L_out, float *dQ, float *dK, float *dV, int N,
                                    int D, float scale, int is_causal, int B, int H, int dtype);
+/* The same with a choice of gradient type on the way out: grad_dtype = -1 keeps the reference's fp32
+ * gradients (kernels.metal:912-914 `atomic_float* dQ/dK/dV`), FA_DTYPE_FP16 / FA_DTYPE_BF16 rounds them on
+ * the device (round to nearest even) so half as many bytes cross PCIe -- the device->host copy of the
+ * fp32 gradients is what bounds the fp32 form of this call.  dQ/dK/dV then point to 16-bit buffers. */
+int fa_host_attention_fwd_bwd_half_ex(const void *Q, const void *K, const void *V, const void *dO, void *O,
+                                      float *L_out, void *dQ, void *dK, void *dV, int N, int D, float scale,
+                                      int is_causal, int B, int H, int dtype, int grad_dtype);
 void fa_host_release(void);
 
 /* ---- support ----------------------------------------------------------------*/

@@ -14,15 +14,23 @@ TOL_ABS = 2e-2
 TOL_REL = {oracle.FP16: 2e-3, oracle.BF16: 1e-2}
 
 
-@pytest.fixture(scope="module")
-def fa():
+@pytest.fixture(scope="module", params=["fused", "two_kernel"])
+def fa(request):
+    """Every test of this file runs on both forms of the backward: the fused five-GEMM kernel
+    (csrc/bwd_fused.cu, the default) and the two-kernel form (csrc/bwd_tc.cu), selected through the
+    library's debug hook."""
+    import ctypes
+
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import flash_attention_metal_b200 as fa
 
-    fa.lib()
-    return fa
+    setter = fa.lib().fa_debug_set_bwd_mode
+    setter.argtypes = [ctypes.c_int]
+    setter(1 if request.param == "two_kernel" else 0)
+    yield fa
+    setter(0)
 
 
 def dev(x):
@@ -147,7 +155,7 @@ def test_backward_workspace_and_argument_errors(fa):
         fa.flash_attention_backward(t, t, t, t, t, L, g, g, g, n, d, 0.125, n * d, n * d, False, 1, 1, fa.BF16, ws, 16)
 
 
-@pytest.mark.parametrize("causal", [True])
+@pytest.mark.parametrize("causal", [True, False])
 def test_backward_flagship_shape_sampled(fa, causal):
     """BASELINE config 3 (bf16, H=16, N=16384, d=128): sampled rows of dQ and sampled keys of
     dK/dV recomputed in fp64 from the same inputs."""

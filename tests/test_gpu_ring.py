@@ -179,6 +179,92 @@ def test_ring_schedule_emulated_on_one_gpu(fa, world, causal):
         assert np.abs(l_acc - want_l[rows]).max() <= 5e-3
 
 
+@pytest.mark.parametrize("world,n_local,d", [(2, 328, 64), (3, 200, 128), (4, 256, 64)])
+@pytest.mark.parametrize("causal", [False, True])
+def test_ring_forward_and_backward_replayed_on_one_gpu(fa, world, n_local, d, causal):
+    """Every rank's ring schedule replayed on one GPU with the kernels and the fused merge exactly as
+    fa_ring_attention_forward / _backward drive them (same block offsets, same merge modes per zig-zag
+    half, dQ accumulated over the steps, dK/dV of a chunk summed over the ranks) -- only the transport is
+    left out.  Chunks of 164 / 100 rows are not multiples of the 128-row tiles."""
+    import ctypes
+    import torch
+
+    fn = fa.lib().fa_debug_forward_partial
+    vp, i32 = ctypes.c_void_p, ctypes.c_int
+    fn.argtypes = [vp] * 7 + [i32, i32, i32, ctypes.c_float, i32, i32, i32, i32, i32, i32, vp]
+    H, n, scale = 2, world * n_local, float(d ** -0.5)
+    c = n_local // 2
+    bits, f = zip(*(bf16(oracle.init_random(H * n * d, s).reshape(H, n, d)) for s in (51, 52, 53, 54)))
+    rows_of = lambda r: np.concatenate([np.arange(a, a + cnt) for a, cnt in fa.ring_local_rows(r, world, n_local, causal)])
+    want_o, want_l = oracle.forward_batched(f[0], f[1], f[2], scale, causal)
+    want_g = [np.stack(x) for x in zip(*(oracle.backward(f[0][h], f[1][h], f[2][h], f[3][h], scale, causal) for h in range(H)))]
+    mode = lambda first, last: 0 if first and last else 1 if first else 3 if last else 2
+    loc = lambda t, r: dev(np.ascontiguousarray(t[:, rows_of(r)]).view(np.int16))
+    Kl = [loc(bits[1], r) for r in range(world)]
+    Vl = [loc(bits[2], r) for r in range(world)]
+    dK_sum = [torch.zeros((H, n_local, d), device="cuda") for _ in range(world)]  # per OWNER rank
+    dV_sum = [torch.zeros((H, n_local, d), device="cuda") for _ in range(world)]
+    hs = n_local * d
+    for rank in range(world):
+        rows = rows_of(rank)
+        Q, dO = loc(bits[0], rank), loc(bits[3], rank)
+        O = torch.zeros((H, n_local, d), dtype=torch.int16, device="cuda")
+        L = torch.zeros((H, n_local), device="cuda")
+        o_acc = torch.full((H, n_local, d), float("nan"), device="cuda")
+        l_acc = torch.full((H, n_local), float("nan"), device="cuda")
+        plan = [fa.ring_plan(rank, world, s, n_local, causal) for s in range(world)]
+        for s, (src, q_off, q_rows, k_off, k_rows, bc) in enumerate(plan):
+            if not causal:
+                lo = hi = mode(s == 0, s == world - 1)
+                half = 0
+            elif q_off == 0:
+                lo, hi, half = mode(s == 0, s == rank), mode(s == 0, s == world - 1), c
+            else:
+                lo = hi = mode(s == 0, s == world - 1)
+                half = 0
+            # the kernel addresses heads with the strides of the full local tensors: call head by head with offsets
+            for h in range(H):
+                qo, ko = (h * n_local + q_off) * d, (h * n_local + k_off) * d
+                rc = fn(Q.data_ptr() + qo * 2, Kl[src].data_ptr() + ko * 2, Vl[src].data_ptr() + ko * 2, O.data_ptr() + qo * 2,
+                        L.data_ptr() + (h * n_local + q_off) * 4, o_acc.data_ptr() + qo * 4, l_acc.data_ptr() + (h * n_local + q_off) * 4,
+                        q_rows, k_rows, d, scale, 1, bc, lo, hi, half, fa.BF16, None)
+                assert rc == 0, fa.lib().fa_last_error()
+        torch.cuda.synchronize()
+        got = oracle.from_half_bits(O.cpu().numpy().view(np.uint16), oracle.BF16)
+        assert np.abs(got - want_o[:, rows]).max() <= TOL
+        assert np.abs(L.cpu().numpy() - want_l[:, rows]).max() <= 5e-3
+        # ---- backward of the same schedule ----
+        delta = torch.zeros((H, n_local), device="cuda")
+        fa.rowsum_delta(O, dO, delta, n_local, d, H * hs, hs, 1, H, fa.BF16)
+        dQ = torch.full((H, n_local, d), float("nan"), device="cuda")
+        for s, (src, q_off, q_rows, k_off, k_rows, bc) in enumerate(plan):
+            tmp_k = torch.zeros((H, n_local, d), device="cuda")
+            tmp_v = torch.zeros((H, n_local, d), device="cuda")
+            for h in range(H):
+                qo, ko = (h * n_local + q_off) * d, (h * n_local + k_off) * d
+                args = (Q.data_ptr() + qo * 2, Kl[src].data_ptr() + ko * 2, Vl[src].data_ptr() + ko * 2, dO.data_ptr() + qo * 2,
+                        L.data_ptr() + (h * n_local + q_off) * 4, delta.data_ptr() + (h * n_local + q_off) * 4,
+                        dQ.data_ptr() + qo * 4, tmp_k.data_ptr() + ko * 4, tmp_v.data_ptr() + ko * 4)
+                if bc:  # the local causal block (step 0): the square backward entry point computes delta itself
+                    wsb = fa.workspace_bytes_backward(q_rows, d, 1, 1)
+                    ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
+                    fa.flash_attention_backward(args[0], args[1], args[2], O.data_ptr() + qo * 2, args[3], args[4], args[6], args[7],
+                                                args[8], q_rows, d, scale, q_rows * d, q_rows * d, True, 1, 1, fa.BF16, ws, wsb)
+                else:
+                    fa.flash_attention_backward_rect(*args, q_rows, k_rows, d, scale, q_rows * d, q_rows * d, k_rows * d, k_rows * d,
+                                                     s > 0, 1, 1, fa.BF16)
+            dK_sum[src] += tmp_k
+            dV_sum[src] += tmp_v
+        torch.cuda.synchronize()
+        err = np.abs(dQ.cpu().numpy() - want_g[0][:, rows]).max()
+        assert err <= 1e-2 * np.abs(want_g[0]).max(), ("dQ", rank, err)
+    for r in range(world):
+        rows = rows_of(r)
+        for got, want, name in ((dK_sum[r], want_g[1], "dK"), (dV_sum[r], want_g[2], "dV")):
+            err = np.abs(got.cpu().numpy() - want[:, rows]).max()
+            assert err <= 1e-2 * np.abs(want).max(), (name, r, err)
+
+
 @pytest.mark.parametrize("causal", [False, True])
 def test_ring_backward_world_one_matches_oracle(fa, causal):
     """fa_ring_attention_backward with a one-rank communicator: delta + rectangular backward kernels."""

@@ -62,3 +62,18 @@ def test_unmodified_reference_plot_script_accepts_the_csv(tmp_path):
     svg = (tmp_path / "speedup_plot.svg").read_text()
     assert svg.lstrip().startswith("<svg") or "<svg" in svg
     assert len(re.findall(r"<(polyline|path|line|circle)", svg)) > 4
+
+
+def test_tflops_plot_script_reads_the_same_csv(tmp_path):
+    """harness/plot_tflops.py (the second plot of row f1: TFLOP/s and % of peak vs N) accepts the harness CSV and
+    also a CSV that only has the reference's ten columns."""
+    script = os.path.join(ROOT, "harness", "plot_tflops.py")
+    out = tmp_path / "tflops.svg"
+    subprocess.check_call([sys.executable, script, CSV, "-o", str(out)], stdout=subprocess.DEVNULL)
+    svg = out.read_text()
+    assert svg.lstrip().startswith("<svg") and svg.count("<polyline") >= 3
+    ten = tmp_path / "benchmark_results_causal.csv"
+    lines = open(CSV).read().splitlines()
+    ten.write_text("\n".join(",".join(l.split(",")[:10]) for l in lines) + "\n")
+    subprocess.check_call([sys.executable, script, str(ten), "-o", str(out)], stdout=subprocess.DEVNULL)
+    assert out.read_text().count("<polyline") >= 3
