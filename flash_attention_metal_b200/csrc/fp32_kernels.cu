@@ -11,6 +11,7 @@
 #include <math_constants.h>
 
 #include "fa_internal.h"
+#include "sm100_ptx.cuh"
 
 namespace fa {
 namespace {
@@ -239,11 +240,11 @@ __global__ void __launch_bounds__(V2_THREADS) flash_attention_v2_kernel(
   load_kv(0, 0);
   cp_async_commit();
 
-  float o[4][OC * 4];
+  uint64_t o2[4][OC * 2];  // output accumulators as fp32x2 pairs: columns (4 oc, 4 oc + 1) and (4 oc + 2, 4 oc + 3)
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int c = 0; c < OC * 4; ++c) o[i][c] = 0.f;
+    for (int c = 0; c < OC * 2; ++c) o2[i][c] = 0ull;
   float m[4], l[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) { m[i] = -CUDART_INF_F; l[i] = 0.f; }
@@ -256,23 +257,38 @@ __global__ void __launch_bounds__(V2_THREADS) flash_attention_v2_kernel(
     __syncthreads();
 
     // ---- S = Q K^T on a 4x4 register tile --------------------------------
+    // packed fp32x2 FMAs (FFMA2: one issue slot for two lanes): each accumulator is a pair of partial
+    // sums over the even / odd pairs of the head dimension, added at the end.  Halves the issue slots of
+    // the FMA-bound loops so the FMA pipe, not the scheduler, is the limit.
     float s[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
-#pragma unroll 4
-    for (int c = 0; c < C4; ++c) {
-      float4 a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4 *>(&sm.q[ty + 16 * i][4 * c]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4 *>(&sm.k[st][tx + 16 * j][4 * c]);
+    {
+      uint64_t s2[4][4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          s[i][j] += a[i].x * b[j].x + a[i].y * b[j].y + a[i].z * b[j].z + a[i].w * b[j].w;
+        for (int j = 0; j < 4; ++j) s2[i][j] = 0ull;
+      const uint32_t q_base = (uint32_t)__cvta_generic_to_shared(&sm.q[ty][0]);
+      const uint32_t k_base = (uint32_t)__cvta_generic_to_shared(&sm.k[st][tx][0]);
+      constexpr uint32_t kRow16 = 16u * V2Smem<D>::LD * 4u;  // byte distance of rows 16 apart
+#pragma unroll 4
+      for (int c = 0; c < C4; ++c) {
+        uint64_t a[4][2], b[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ptx::lds_v2b64(q_base + i * kRow16 + c * 16, a[i][0], a[i][1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ptx::lds_v2b64(k_base + j * kRow16 + c * 16, b[j][0], b[j][1]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s2[i][j] = ptx::fma_f32x2(a[i][0], b[j][0], s2[i][j]);
+            s2[i][j] = ptx::fma_f32x2(a[i][1], b[j][1], s2[i][j]);
+          }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = ptx::lo_f32(s2[i][j]) + ptx::hi_f32(s2[i][j]);
     }
     // ---- mask + online softmax -------------------------------------------
     const bool need_mask = (j0 + V2_BN > N) || (is_causal && j0 + V2_BN - 1 > row0);
@@ -294,8 +310,9 @@ __global__ void __launch_bounds__(V2_THREADS) flash_attention_v2_kernel(
       const float corr = exp2f((m[i] - m_ref) * scale_log2);
       m[i] = m_new;
       l[i] *= corr;
+      const uint64_t corr2 = ptx::pack_f32x2(corr, corr);
 #pragma unroll
-      for (int c = 0; c < OC * 4; ++c) o[i][c] *= corr;
+      for (int c = 0; c < OC * 2; ++c) o2[i][c] = ptx::mul_f32x2(o2[i][c], corr2);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float p = exp2f((s[i][j] - m_ref) * scale_log2);
@@ -305,23 +322,36 @@ __global__ void __launch_bounds__(V2_THREADS) flash_attention_v2_kernel(
     }
     __syncwarp();
     // ---- O += P V ----------------------------------------------------------
+    {
+      const uint32_t p_base = (uint32_t)__cvta_generic_to_shared(&sm.p[ty][0]);
+      const uint32_t v_base = (uint32_t)__cvta_generic_to_shared(&sm.v[st][0][4 * tx]);
+      constexpr uint32_t kPRow16 = 16u * (V2_BN + 4) * 4u, kVRow = V2Smem<D>::LD * 4u;
 #pragma unroll 2
-    for (int k4 = 0; k4 < V2_BN / 4; ++k4) {
-      float4 p[4];
+      for (int k4 = 0; k4 < V2_BN / 4; ++k4) {
+        float4 p[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) p[i] = *reinterpret_cast<const float4 *>(&sm.p[ty + 16 * i][4 * k4]);
+        for (int i = 0; i < 4; ++i) {
+          uint64_t lo, hi;
+          ptx::lds_v2b64(p_base + i * kPRow16 + k4 * 16, lo, hi);
+          p[i] = make_float4(ptx::lo_f32(lo), ptx::hi_f32(lo), ptx::lo_f32(hi), ptx::hi_f32(hi));
+        }
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-#pragma unroll
-        for (int oc = 0; oc < OC; ++oc) {
-          const float4 vv = *reinterpret_cast<const float4 *>(&sm.v[st][4 * k4 + kk][64 * oc + 4 * tx]);
+        for (int kk = 0; kk < 4; ++kk) {
+          uint64_t pp[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float pv = kk == 0 ? p[i].x : kk == 1 ? p[i].y : kk == 2 ? p[i].z : p[i].w;
-            o[i][4 * oc + 0] += pv * vv.x;
-            o[i][4 * oc + 1] += pv * vv.y;
-            o[i][4 * oc + 2] += pv * vv.z;
-            o[i][4 * oc + 3] += pv * vv.w;
+            pp[i] = ptx::pack_f32x2(pv, pv);
+          }
+#pragma unroll
+          for (int oc = 0; oc < OC; ++oc) {
+            uint64_t v01, v23;
+            ptx::lds_v2b64(v_base + (4 * k4 + kk) * kVRow + oc * 256, v01, v23);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              o2[i][2 * oc] = ptx::fma_f32x2(pp[i], v01, o2[i][2 * oc]);
+              o2[i][2 * oc + 1] = ptx::fma_f32x2(pp[i], v23, o2[i][2 * oc + 1]);
+            }
           }
         }
       }
@@ -341,8 +371,8 @@ __global__ void __launch_bounds__(V2_THREADS) flash_attention_v2_kernel(
 #pragma unroll
       for (int oc = 0; oc < OC; ++oc)
         *reinterpret_cast<float4 *>(O + (int64_t)gi * D + 64 * oc + 4 * tx) =
-            make_float4(o[i][4 * oc] * inv, o[i][4 * oc + 1] * inv, o[i][4 * oc + 2] * inv,
-                        o[i][4 * oc + 3] * inv);
+            make_float4(ptx::lo_f32(o2[i][2 * oc]) * inv, ptx::hi_f32(o2[i][2 * oc]) * inv,
+                        ptx::lo_f32(o2[i][2 * oc + 1]) * inv, ptx::hi_f32(o2[i][2 * oc + 1]) * inv);
     }
   }
 }
