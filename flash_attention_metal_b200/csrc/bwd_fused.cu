@@ -79,7 +79,24 @@ struct FusedParams {
   int causal;          // requires Nq == Nk
   int acc_dq;          // dQ += (ring attention) instead of dQ =
   int group, n_heads;  // dispatch order (sched.cuh)
+#ifdef FA_BWD_TRACE
+  long long *prof;     // trace builds only: where one CTA's roles waited (cycles), see tests/fused_probe.py
+#endif
 };
+
+// FA_BWD_TRACE (development builds only): the CTA of key tile 8 of head 0 accumulates the cycles each of
+// its roles spends in every wait.  T_BEGIN(var) ... T_END(var, slot) bracket a region.
+#ifdef FA_BWD_TRACE
+#define T_DECL(on) const bool t_on = p.prof != nullptr && (on); long long t_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long t_0 = 0, t_start = t_on ? clock64() : 0
+#define T_BEGIN() do { if (t_on) t_0 = clock64(); } while (0)
+#define T_END(slot) do { if (t_on) t_acc[slot] += clock64() - t_0; } while (0)
+#define T_FLUSH(base, count) do { if (t_on) { for (int t_i = 0; t_i < (count); ++t_i) p.prof[(base) + t_i] = t_acc[t_i]; p.prof[(base) + (count)] = clock64() - t_start; } } while (0)
+#else
+#define T_DECL(on) do {} while (0)
+#define T_BEGIN() do {} while (0)
+#define T_END(slot) do {} while (0)
+#define T_FLUSH(base, count) do {} while (0)
+#endif
 
 template <int D>
 struct FusedCfg {
@@ -154,6 +171,9 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const int n = n_q_tiles - t_lo;          // pairs of this CTA, query tile of pair m: n_q_tiles - 1 - m
   const int64_t kv_off = (int64_t)b * p.kv_batch_stride + (int64_t)h * p.kv_head_stride;
   const int64_t vec_off = ((int64_t)b * p.batch_stride + (int64_t)h * p.head_stride) / D;
+#ifdef FA_BWD_TRACE
+  const bool traced_cta = j == 8 && h == 0 && b == 0;
+#endif
 
   if (threadIdx.x == 0) {
     mbar_init(res_full, 1);
@@ -206,36 +226,49 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t ds_row = smem_u32(sDS) + wg * Cfg::kChunk + tid * 128;
     const uint32_t box_row = smem_u32(sBox) + wg * Cfg::kBoxBytes + tid * 128;
     const uint32_t sw = (uint32_t)(tid & 7);
+    T_DECL(traced_cta && tid == 0 && wg == 0);  // slots: 0 x_full 1 phase1 2 dq_full 3 stage_free(A) 4 y_full 5 phase2 6 stage_free(B) 7 stats barrier
     int fills = 0;  // staging-box fills of this warpgroup so far
-    // dQ block of pair m: TMEM -> registers (frees the TMEM block) -> staging box(es) -> reducer warp
-    auto drain_dq = [&](int m) {
-      mbar_wait(dq_full, m & 1);
-      tc_fence_after();
-      uint32_t v[Cfg::kBoxesPerWg][32];
+    // dQ block of a pair: TMEM -> registers (frees the TMEM block) -> staging box -> reducer warp.  The
+    // warpgroup has ONE 16 KB box; at D = 128 it fills it twice per pair.  The second fill has to wait
+    // until the TMA engine has read the first, so it is deferred until after phase 2 of the current pair
+    // (the values wait in registers) instead of stalling here.
+    uint32_t dqv[Cfg::kBoxesPerWg][32];
+    auto fill_box = [&](int hb) {
+      T_BEGIN();
+      if (fills > 0) mbar_wait(&stage_free[wg], (fills - 1) & 1);
+      T_END(hb == 0 ? 3 : 6);
 #pragma unroll
-      for (int hb = 0; hb < Cfg::kBoxesPerWg; ++hb) tmem_ld32(tDQ + hb * 32, v[hb]);
+      for (int u = 0; u < 8; ++u)
+        sts_v4(box_row + ((u ^ sw) << 4), dqv[hb][4 * u], dqv[hb][4 * u + 1], dqv[hb][4 * u + 2], dqv[hb][4 * u + 3]);
+      fence_proxy_async();
+      mbar_arrive_warp(&stage_full[wg]);
+      ++fills;
+    };
+    auto drain_dq = [&](int m) {
+      T_BEGIN();
+      mbar_wait(dq_full, m & 1);
+      T_END(2);
+      tc_fence_after();
+#pragma unroll
+      for (int hb = 0; hb < Cfg::kBoxesPerWg; ++hb) tmem_ld32(tDQ + hb * 32, dqv[hb]);
       tmem_wait_ld();
       tc_fence_before();
       mbar_arrive_warp(dq_drained);
-#pragma unroll
-      for (int hb = 0; hb < Cfg::kBoxesPerWg; ++hb) {
-        if (fills > 0) mbar_wait(&stage_free[wg], (fills - 1) & 1);
-#pragma unroll
-        for (int u = 0; u < 8; ++u)
-          sts_v4(box_row + ((u ^ sw) << 4), v[hb][4 * u], v[hb][4 * u + 1], v[hb][4 * u + 2], v[hb][4 * u + 3]);
-        fence_proxy_async();
-        mbar_arrive_warp(&stage_full[wg]);
-        ++fills;
-      }
+      fill_box(0);
     };
     for (int m = 0; m < n; ++m) {
       const int q0 = (n_q_tiles - 1 - m) * 128 + wg * 64;  // first query column of this warpgroup's half
       float *ld = sLD + (wg * 2 + (m & 1)) * 128;
+      T_BEGIN();
       ld[tid] = stat_next * stat_coef;
       stat_next = fetch_stat(m + 1);
       named_bar_sync(1 + wg, 128);
+      T_END(7);
       // ---- phase 1: P^T = exp2(S^T * c - L * log2e) ----
+      T_BEGIN();
       mbar_wait(x_full, m & 1);
+      T_END(0);
+      T_BEGIN();
       tc_fence_after();
       uint32_t pr[2][32];  // S^T, then P^T (fp32 bits), kept for phase 2
       tmem_ld32(tX, pr[0]);
@@ -278,10 +311,14 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_before();
         mbar_arrive_warp(&p_ready[c]);
       }
-      // ---- the previous pair's dQ block leaves TMEM (Y(m) was only issued after this drain) ----
+      T_END(1);
+      // ---- the previous pair's dQ block leaves TMEM (Y(m) is only issued after this drain) ----
       if (m > 0) drain_dq(m - 1);
       // ---- phase 2: dS^T = P^T o (dP^T * scale - D * scale) ----
+      T_BEGIN();
       mbar_wait(y_full, m & 1);
+      T_END(4);
+      T_BEGIN();
       tc_fence_after();
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -309,8 +346,15 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tc_fence_before();
         mbar_arrive_warp(&ds_ready[c]);
       }
+      T_END(5);
+      if (Cfg::kBoxesPerWg == 2 && m > 0) fill_box(1);  // second half of the previous pair's dQ block
     }
     drain_dq(n - 1);
+    if (Cfg::kBoxesPerWg == 2) fill_box(1);
+    T_FLUSH(0, 8);
+#ifdef FA_BWD_TRACE
+    if (t_on) p.prof[63] = n;
+#endif
     // ------------------------------ epilogue ------------------------------
     mbar_wait(acc_full, 0);
     tc_fence_after();
@@ -359,10 +403,13 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV), sQ_a = smem_u32(sQ), sDO_a = smem_u32(sDO), sDS_a = smem_u32(sDS);
         const uint32_t tX = tmem_base, tY = tmem_base + 128, tdV = tmem_base + Cfg::kTmemDV, tdK = tmem_base + Cfg::kTmemDK,
                        tdQ = tmem_base + Cfg::kTmemDQ;
+        T_DECL(traced_cta);  // slots: 0 q_full 1 do_full 2 p_ready 3 ds_ready 4 dq_drained
         auto q_addr = [&](int m) { return sQ_a + (m % Cfg::kQSlots) * Cfg::kTile; };
         auto do_addr = [&](int m) { return sDO_a + (m % Cfg::kDoSlots) * Cfg::kTile; };
         auto issue_x = [&](int m) {  // S^T = K Q^T
+          T_BEGIN();
           mbar_wait(&q_full[m % Cfg::kQSlots], (m / Cfg::kQSlots) & 1);
+          T_END(0);
           tc_fence_after();
 #pragma unroll
           for (int kk = 0; kk < D / 16; ++kk)
@@ -378,10 +425,14 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_commit(y_full);
         };
         auto issue_dv = [&](int m) {  // dV += P^T dO (K = 128 query rows); part c = k-steps {2c, 2c+1, 4+2c, 5+2c}
+          T_BEGIN();
           mbar_wait(&do_full[m % Cfg::kDoSlots], (m / Cfg::kDoSlots) & 1);
+          T_END(1);
 #pragma unroll
           for (int part = 0; part < 2; ++part) {
+            T_BEGIN();
             mbar_wait(&p_ready[part], m & 1);
+            T_END(2);
             tc_fence_after();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -402,7 +453,9 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           // dK += dS^T Q (A from TMEM), then the dQ block = dS K (both operands from shared memory)
 #pragma unroll
           for (int part = 0; part < 2; ++part) {
+            T_BEGIN();
             mbar_wait(&ds_ready[part], m & 1);
+            T_END(3);
             tc_fence_after();
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -420,12 +473,15 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           tc_commit(dq_full);
           if (m + 1 < n) {
             issue_dv(m + 1);
+            T_BEGIN();
             mbar_wait(dq_drained, m & 1);  // the dQ block (over Y at D = 128) has left TMEM
+            T_END(4);
             tc_fence_after();
             issue_y(m + 1);
             tc_commit(&do_empty[(m + 1) % Cfg::kDoSlots]);
           }
         }
+        T_FLUSH(16, 5);
       }
       __syncwarp();
     } else if (warp == kDqWarp) {
@@ -434,40 +490,55 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         prefetch_tensormap(&tmdQ);
         uint32_t *sem = p.sems + (size_t)(b * p.H + h) * n_q_tiles;
         const bool store_first = (j == 0) && !p.acc_dq;  // key tile 0 is the first contributor of every dQ tile
-        int fills[2] = {0, 0};
+        T_DECL(traced_cta);  // slots: 0 stage_full 1 ordering counter 2 read wait 3 completion wait
+        int fills = 0;  // fills consumed per warpgroup (both advance together)
         for (int m = 0; m < n; ++m) {
           const int ti = n_q_tiles - 1 - m;
-          bool ordered = false;
 #pragma unroll
           for (int hb = 0; hb < Cfg::kBoxesPerWg; ++hb) {
 #pragma unroll
             for (int w = 0; w < 2; ++w) {
-              mbar_wait(&stage_full[w], fills[w] & 1);
-              if (!ordered) {
+              T_BEGIN();
+              mbar_wait(&stage_full[w], fills & 1);
+              T_END(0);
+              T_BEGIN();
+              if (hb == 0 && w == 0 && j > 0) {
                 // my turn: key tiles 0 .. j-1 have finished adding their part of dQ tile ti
-                if (j > 0) {
-                  const long long t0 = clock64();
-                  while (ld_acquire_gpu(sem + ti) < (uint32_t)j) {
-                    __nanosleep(100);
-                    if (clock64() - t0 > 4000000000LL) __trap();
-                  }
+                const long long t0 = clock64();
+                while (ld_acquire_gpu(sem + ti) < (uint32_t)j) {
+                  __nanosleep(100);
+                  if (clock64() - t0 > 4000000000LL) __trap();
                 }
-                ordered = true;
               }
+              T_END(1);
               const unsigned char *box = sBox + w * Cfg::kBoxBytes;
               const int col = w * (D / 2) + hb * 32;
               if (store_first) tma_store_4d(&tmdQ, box, col, ti * 128, h, b);
               else tma_reduce_add_4d(&tmdQ, box, col, ti * 128, h, b);
               bulk_commit_group();
-              bulk_wait_read_all();
-              mbar_arrive(&stage_free[w]);
-              ++fills[w];
             }
+            T_BEGIN();
+            bulk_wait_read_all();  // both boxes have been read: the warpgroups may refill them
+            T_END(2);
+            mbar_arrive(&stage_free[0]);
+            mbar_arrive(&stage_free[1]);
+            ++fills;
           }
-          bulk_wait_all();            // this CTA's part of dQ tile ti is in memory
-          __threadfence();
-          red_release_gpu_add(sem + ti, 1u);
+          // The groups of pair m are in flight; those of pair m - 1 are complete once at most this pair's
+          // groups are pending: only then may the next key tile add to dQ tile ti + 1 (release, one pair late,
+          // instead of idling here until the L2 has performed this pair's reduction).
+          if (m > 0) {
+            T_BEGIN();
+            bulk_wait_pending<2 * Cfg::kBoxesPerWg>();
+            T_END(3);
+            __threadfence();
+            red_release_gpu_add(sem + ti + 1, 1u);
+          }
         }
+        bulk_wait_all();
+        __threadfence();
+        red_release_gpu_add(sem + (n_q_tiles - n), 1u);  // the last pair's query tile
+        T_FLUSH(32, 4);
       }
       __syncwarp();
     }
@@ -536,6 +607,9 @@ int launch_bwd_fused(const void *Q, const void *K, const void *V, const void *dO
   p.kv_head_stride = kv_head_stride;
   p.causal = is_causal ? 1 : 0;
   p.acc_dq = acc_dq ? 1 : 0;
+#ifdef FA_BWD_TRACE
+  p.prof = g_trace_buffer;
+#endif
   if (D == 64)
     return dtype == FA_DTYPE_BF16 ? launch_impl<64, 1>(maps, p, B, stream) : launch_impl<64, 0>(maps, p, B, stream);
   return dtype == FA_DTYPE_BF16 ? launch_impl<128, 1>(maps, p, B, stream) : launch_impl<128, 0>(maps, p, B, stream);

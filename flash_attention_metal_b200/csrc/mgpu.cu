@@ -146,6 +146,12 @@ int fa_mgpu_create(void **out, const int *devices, int n_devices) {
   return FA_OK;
 }
 
+// Development aid (not in the public header): the ring object of the index-th device (for fa_debug_ring_flags)
+void *fa_debug_mgpu_ring(void *group, int index) {
+  MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
+  return (g && index >= 0 && index < g->n) ? g->rings[index] : nullptr;
+}
+
 int fa_mgpu_destroy(void *group) {
   group_free(reinterpret_cast<MgpuGroup *>(group));
   return FA_OK;

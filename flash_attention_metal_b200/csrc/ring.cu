@@ -411,6 +411,20 @@ using namespace fa;
 
 extern "C" {
 
+// Development aids (not in the public header): which of the three peer-flag write mechanisms this process
+// settled on (0 stream write to the peer address, 1 32-bit memset of it, 2 local stream write + 4-byte
+// peer copy), and a way to force one.
+int fa_debug_ring_write_mechanism(void) { return g_write_mech.load(std::memory_order_relaxed); }
+void fa_debug_set_ring_write_mechanism(int m) { g_write_mech.store(m < 0 ? 0 : (m > 2 ? 2 : m), std::memory_order_relaxed); }
+// copy of the first n flag words of a ring (synchronous)
+int fa_debug_ring_flags(void *ring, uint32_t *out, int n) {
+  Ring *r = reinterpret_cast<Ring *>(ring);
+  FA_REQUIRE(r && r->flags && out && n > 0 && n <= 1024, "bad arguments");
+  FA_CUDA_CHECK(cudaSetDevice(r->device));
+  FA_CUDA_CHECK(cudaMemcpy(out, r->flags, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return FA_OK;
+}
+
 int fa_ring_unique_id_bytes(void) { return (int)sizeof(NcclUniqueId); }
 
 int fa_ring_get_unique_id(void *out, int bytes) {

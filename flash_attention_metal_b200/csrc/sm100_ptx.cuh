@@ -127,6 +127,9 @@ __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bul
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 // all bulk groups of this thread are complete (their global writes are performed)
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+// all but the N most recent bulk groups of this thread are complete
+template <int N>
+__device__ __forceinline__ void bulk_wait_pending() { asm volatile("cp.async.bulk.wait_group %0;\n" ::"n"(N) : "memory"); }
 
 // ---- cross-CTA ordering through a counter in global memory ----
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t *p) {
