@@ -22,6 +22,8 @@ FP16, BF16 = 0, 1
 NAIVE, V1, V2 = 0, 1, 2
 #: ring transports (FA_RING_TRANSPORT_* of the header)
 TRANSPORT_AUTO, TRANSPORT_NCCL, TRANSPORT_NCCL_GATHER, TRANSPORT_PEER = 0, 1, 2, 3
+#: backward implementations (fa_set_backward_algorithm)
+BWD_TWO_KERNEL, BWD_FUSED = 0, 1
 
 #: every symbol include/flash_attn_b200.h declares (tests check they are all exported)
 EXPORTS = (
@@ -36,7 +38,8 @@ EXPORTS = (
     "flash_attention_backward_rect", "fa_rowsum_delta",
     "fa_mgpu_create", "fa_mgpu_destroy", "fa_mgpu_device_count", "fa_mgpu_stream", "fa_mgpu_synchronize",
     "fa_mgpu_sharded_forward", "fa_mgpu_sharded_backward", "fa_mgpu_ring_forward", "fa_mgpu_ring_backward",
-    "fa_last_error", "fa_version", "fa_device_count", "fa_launch_count", "fa_reset_launch_count",
+    "fa_last_error", "fa_version", "fa_device_count", "fa_preload_kernels", "fa_set_backward_algorithm",
+    "fa_get_backward_algorithm", "fa_launch_count", "fa_reset_launch_count",
 )
 
 
@@ -75,6 +78,7 @@ def lib() -> C.CDLL:
         L.fa_host_attention_half.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, i32, i32, i32, i32]
         L.fa_host_attention_fwd_bwd_half.argtypes = [vp] * 9 + [i32, i32, f32, i32, i32, i32, i32]
         L.fa_host_attention_fwd_bwd_half_ex.argtypes = [vp] * 9 + [i32, i32, f32, i32, i32, i32, i32, i32]
+        L.fa_set_backward_algorithm.argtypes = [i32]
         L.fa_host_release.restype = None
         L.fa_last_error.restype = C.c_char_p
         L.fa_launch_count.restype = C.c_long
@@ -297,6 +301,15 @@ def flash_attention_backward_rect(Q, K, V, dO, L, delta, dQ, dK, dV, Nq, Nk, D, 
 def rowsum_delta(O, dO, delta, N, D, batch_stride, head_stride, B=1, H=1, dtype=FP16, stream=None):
     """delta[b, h, i] = sum_d O * dO (kernels.metal:983-990)."""
     _check(lib().fa_rowsum_delta(_ptr(O), _ptr(dO), _ptr(delta), N, D, batch_stride, head_stride, B, H, dtype, _stream(stream)))
+
+
+def set_backward_algorithm(algorithm: int) -> None:
+    """BWD_TWO_KERNEL (default) or BWD_FUSED; process-wide."""
+    _check(lib().fa_set_backward_algorithm(algorithm))
+
+
+def get_backward_algorithm() -> int:
+    return int(lib().fa_get_backward_algorithm())
 
 
 def workspace_bytes_backward(N, D, B, H) -> int:

@@ -34,6 +34,12 @@ int bwd_mode() { return g_bwd_mode.load(std::memory_order_relaxed); }
 static std::atomic<int> g_l2_group_mb{48};
 int l2_group_mb() { return g_l2_group_mb.load(std::memory_order_relaxed); }
 
+int preload_kernels() {
+  int rc;
+  if ((rc = preload_fwd_tc()) || (rc = preload_bwd_tc()) || (rc = preload_bwd_fused()) || (rc = preload_ring())) return rc;
+  return FA_OK;
+}
+
 int device_sm_count() {
   static std::atomic<int> cache[64];
   int dev = 0;
@@ -74,9 +80,12 @@ int fa_debug_forward_partial(const void *Q, const void *K, const void *V, void *
                             (int64_t)Nk * D, is_causal, 1, H, dtype, (cudaStream_t)stream, &m);
 }
 
-// Development aid (not in the public header): 1 forces the two-kernel backward (bwd_tc.cu), 0 restores
-// the default (the fused kernel of bwd_fused.cu wherever it applies).  Tests run both.
-void fa_debug_set_bwd_mode(int mode) { g_bwd_mode.store(mode, std::memory_order_relaxed); }
+int fa_set_backward_algorithm(int algorithm) {
+  FA_REQUIRE(algorithm == FA_BWD_TWO_KERNEL || algorithm == FA_BWD_FUSED, "unknown backward algorithm %d", algorithm);
+  g_bwd_mode.store(algorithm, std::memory_order_relaxed);
+  return FA_OK;
+}
+int fa_get_backward_algorithm(void) { return g_bwd_mode.load(std::memory_order_relaxed); }
 
 // Development aid (not in the public header): L2 budget of a dispatch group of heads, in MB.
 void fa_debug_set_l2_group_mb(int mb) { g_l2_group_mb.store(mb < 0 ? 0 : mb, std::memory_order_relaxed); }
@@ -92,6 +101,8 @@ void fa_debug_dispatch(int uneven_work, long long streamed_bytes_per_head, int n
   const dim3 g = dispatch_grid(group, n_blocks, H, B);
   out[0] = group; out[1] = (int)g.x; out[2] = (int)g.y; out[3] = (int)g.z;
 }
+
+int fa_preload_kernels(void) { return preload_kernels(); }
 
 int fa_device_count(void) {
   int n = 0;

@@ -550,13 +550,20 @@ bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 }
 
 template <int D, int IS_BF16>
-int launch_impl(const CUtensorMap *const *maps, const FusedParams &p, int B, cudaStream_t stream) {
+int configure() {
   static DeviceOnce configured;
-  const int rc = configured.run([] {
+  return configured.run([] {
     FA_CUDA_CHECK(cudaFuncSetAttribute(bwd_fused_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        FusedCfg<D>::kSmemBytes));
+    cudaFuncAttributes attr;  // forces the (lazily loaded) kernel into the context
+    FA_CUDA_CHECK(cudaFuncGetAttributes(&attr, bwd_fused_kernel<D, IS_BF16>));
     return (int)FA_OK;
   });
+}
+
+template <int D, int IS_BF16>
+int launch_impl(const CUtensorMap *const *maps, const FusedParams &p, int B, cudaStream_t stream) {
+  const int rc = configure<D, IS_BF16>();
   if (rc != FA_OK) return rc;
   FusedParams q = p;
   q.n_heads = B * p.H;
@@ -573,6 +580,12 @@ int launch_impl(const CUtensorMap *const *maps, const FusedParams &p, int B, cud
 }
 
 }  // namespace
+
+int preload_bwd_fused() {
+  int rc;
+  if ((rc = configure<64, 0>()) || (rc = configure<64, 1>()) || (rc = configure<128, 0>()) || (rc = configure<128, 1>())) return rc;
+  return FA_OK;
+}
 
 size_t bwd_fused_sem_bytes(int Nq, int B, int H) {
   const size_t n = (size_t)B * H * ((Nq + 127) / 128) * sizeof(uint32_t);

@@ -57,6 +57,23 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef FA_BWD_SPLIT
 #define FA_BWD_SPLIT 1
 #endif
+// Tuning knobs of the dK/dV kernel's element-wise loop (A/B-ed on B200, tests/bwd_ab.py):
+//   FA_DKDV_LATE_BAR  the warpgroup barrier that publishes the per-column statistics is taken after the
+//                     wait for S^T instead of before it (two idle periods overlap instead of adding up)
+//   FA_DKDV_Y_AHEAD   both halves of dP^T are loaded from TMEM before phase 2 computes (one exposed TMEM
+//                     round trip per tile instead of two)
+//   FA_BWD_REGS_WIDE  registers of the element-wise warps after setmaxnreg (the other warpgroup gets the rest
+//                     of 12 x 168: 216 -> 72, 208 -> 88)
+#ifndef FA_DKDV_LATE_BAR
+#define FA_DKDV_LATE_BAR 0
+#endif
+#ifndef FA_DKDV_Y_AHEAD
+#define FA_DKDV_Y_AHEAD 0
+#endif
+#ifndef FA_BWD_REGS_WIDE
+#define FA_BWD_REGS_WIDE 216
+#endif
+constexpr int kBwdRegsWide = FA_BWD_REGS_WIDE, kBwdRegsNarrow = FA_BWD_REGS_WIDE == 216 ? 64 : (2016 - 8 * FA_BWD_REGS_WIDE) / 4;
 constexpr int kBwdEmu = FA_BWD_EMU;
 constexpr int kDkdvParts = FA_BWD_SPLIT ? 2 : 1;  // hand-offs per phase in bwd_dkdv_kernel
 constexpr int kDqParts = FA_BWD_SPLIT ? 4 : 1;    // dS hand-offs per item in bwd_dq_kernel
@@ -240,7 +257,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp < 8) {
     // ======================= element-wise warpgroups =======================
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<kBwdRegsWide>();
     const int wg = warp >> 2;
     const int tid = (warp & 3) * 32 + lane;  // TMEM lane = key row within the tile
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
@@ -278,11 +295,12 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ld[tid] = stat_next * stat_coef;
       FA_PCLK(cb);
       stat_next = fetch_stat(i + 1);
-      named_bar_sync(1 + wg, 128);
+      if (!FA_DKDV_LATE_BAR) named_bar_sync(1 + wg, 128);
       FA_PDO(t_top += cb - ca; t_top2 += clock64() - cb);
       // ---- phase 1: P^T = exp2(S^T * c - L * log2e) ----
       FA_PCLK(c0);
       mbar_wait(x_full, i & 1);
+      if (FA_DKDV_LATE_BAR) named_bar_sync(1 + wg, 128);
       FA_PCLK(c1);
       tc_fence_after();
       uint32_t pr[2][32];  // S^T, then P^T (fp32 bits), kept for phase 2
@@ -335,11 +353,20 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(y_full, i & 1);
       FA_PCLK(c3);
       tc_fence_after();
+      uint32_t yy[2][32];
+      if (FA_DKDV_Y_AHEAD) {
+        tmem_ld32(tY, yy[0]);
+        tmem_ld32(tY + 32, yy[1]);
+        tmem_wait_ld();
+      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t y[32], dk[16];
-        tmem_ld32(tY + c * 32, y);
-        tmem_wait_ld();
+        uint32_t dk[16];
+        uint32_t (&y)[32] = yy[c];
+        if (!FA_DKDV_Y_AHEAD) {
+          tmem_ld32(tY + c * 32, y);
+          tmem_wait_ld();
+        }
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
           uint64_t da, db;  // -D*scale of four consecutive query columns
@@ -387,7 +414,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    setmaxnreg_dec<64>();
+    setmaxnreg_dec<kBwdRegsNarrow>();
     if (warp == kLoadWarp) {
       // ============================ TMA producer ============================
       if (elect_one()) {
@@ -573,7 +600,7 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
   if (warp < 8) {
     // ======================= element-wise warpgroups =======================
-    setmaxnreg_inc<216>();
+    setmaxnreg_inc<kBwdRegsWide>();
     const int t = warp >> 2;
     const int tid = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
@@ -673,7 +700,7 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
     }
   } else {
-    setmaxnreg_dec<64>();
+    setmaxnreg_dec<kBwdRegsNarrow>();
     if (warp == kLoadWarp) {
       if (elect_one()) {
         prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
@@ -774,15 +801,24 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 }
 
 template <int D, int IS_BF16>
-int launch_bwd_impl(const CUtensorMap *const *maps, const BwdParams &p, int B, cudaStream_t stream) {
+int configure_bwd() {
   static DeviceOnce configured;  // the attribute is per device
-  const int rc = configured.run([] {
+  return configured.run([] {
     FA_CUDA_CHECK(cudaFuncSetAttribute(bwd_dkdv_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        DkdvCfg<D>::kSmemBytes));
     FA_CUDA_CHECK(cudaFuncSetAttribute(bwd_dq_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        DqCfg<D>::kSmemBytes));
+    cudaFuncAttributes attr;  // forces the (lazily loaded) kernels into the context
+    FA_CUDA_CHECK(cudaFuncGetAttributes(&attr, bwd_dkdv_kernel<D, IS_BF16>));
+    FA_CUDA_CHECK(cudaFuncGetAttributes(&attr, bwd_dq_kernel<D, IS_BF16>));
+    FA_CUDA_CHECK(cudaFuncGetAttributes(&attr, bwd_delta_kernel<D, IS_BF16>));
     return (int)FA_OK;
   });
+}
+
+template <int D, int IS_BF16>
+int launch_bwd_impl(const CUtensorMap *const *maps, const BwdParams &p, int B, cudaStream_t stream) {
+  const int rc = configure_bwd<D, IS_BF16>();
   if (rc != FA_OK) return rc;
   // maps: [0] Q, [1] K, [2] V, [3] dO, all with 128-row boxes
   BwdParams q = p;
@@ -805,6 +841,13 @@ int launch_bwd_impl(const CUtensorMap *const *maps, const BwdParams &p, int B, c
 }
 
 }  // namespace
+
+int preload_bwd_tc() {
+  int rc;
+  if ((rc = configure_bwd<64, 0>()) || (rc = configure_bwd<64, 1>()) || (rc = configure_bwd<128, 0>()) || (rc = configure_bwd<128, 1>()))
+    return rc;
+  return FA_OK;
+}
 
 // D_i = rowsum(O o dO) into `delta` ([B, H, Nq] addressed like L: offset / D + row)
 int launch_bwd_delta(const void *O, const void *dO, float *delta, int Nq, int D, int64_t batch_stride,
@@ -846,10 +889,11 @@ int launch_bwd_tc_rect(const void *Q, const void *K, const void *V, const void *
   FA_REQUIRE((H == 1 || (q_head_stride >= (int64_t)Nq * D && kv_head_stride >= (int64_t)Nk * D)) &&
                  (B == 1 || (q_batch_stride >= (int64_t)Nq * D && kv_batch_stride >= (int64_t)Nk * D)),
              "heads overlap: stride smaller than N*D");
-  // One fused kernel (five GEMMs per tile pair, dQ by ordered TMA add-reduction, bwd_fused.cu) when all
-  // three gradients are wanted and the caller provided the ordering counters; otherwise the two-kernel
-  // form below (seven GEMMs, every gradient tile owned by one CTA).
-  if (fused_sems != nullptr && dQ != nullptr && dK != nullptr && bwd_mode() != 1)
+  // Default: the two-kernel form below (seven GEMMs, every gradient tile owned by one CTA) -- the faster
+  // one on B200 for every shape that fills the GPU.  fa_set_backward_algorithm(
+  // FA_BWD_FUSED) selects the single fused kernel (five GEMMs per tile pair, dQ by ordered TMA
+  // add-reduction, bwd_fused.cu) when all three gradients are wanted and the workspace holds its counters.
+  if (bwd_mode() == FA_BWD_FUSED && fused_sems != nullptr && dQ != nullptr && dK != nullptr)
     return launch_bwd_fused(Q, K, V, dO, L, delta, dQ, dK, dV, Nq, Nk, D, scale, q_batch_stride, q_head_stride,
                             kv_batch_stride, kv_head_stride, is_causal, acc_dq, B, H, dtype, fused_sems, stream);
   const CUtensorMap *maps[4];

@@ -51,6 +51,16 @@ struct DeviceOnce {
 // 126 MB L2; only tests change it (fa_debug_set_l2_group_mb) to prove results do not depend on it.
 int l2_group_mb();
 
+// Load every tensor-core / ring kernel into the current device's context and apply the per-device function
+// attributes.  With CUDA's lazy module loading a kernel is otherwise loaded at its first launch, which
+// synchronises the context -- fatal once a stream of that context is parked on a flag that a later enqueue has
+// yet to write (single-process multi-GPU ring).  fa_mgpu_create runs it for every device of the group.
+int preload_fwd_tc();
+int preload_bwd_tc();
+int preload_bwd_fused();
+int preload_ring();
+int preload_kernels();
+
 // SM count of the current device (cached per device, thread-safe; 148 if the query fails)
 int device_sm_count();
 
@@ -107,7 +117,7 @@ int launch_bwd_fused(const void *Q, const void *K, const void *V, const void *dO
                      float *dQ, float *dK, float *dV, int Nq, int Nk, int D, float scale, int64_t q_batch_stride,
                      int64_t q_head_stride, int64_t kv_batch_stride, int64_t kv_head_stride, int is_causal, int acc_dq,
                      int B, int H, int dtype, void *sems, cudaStream_t stream);
-// 0 auto (fused when possible), 1 always the two-kernel form, 2 as 0 (reserved); fa_debug_set_bwd_mode
+// FA_BWD_TWO_KERNEL (default) or FA_BWD_FUSED: fa_set_backward_algorithm
 int bwd_mode();
 
 }  // namespace fa

@@ -639,16 +639,24 @@ int max_cluster_size() {
 // whole-SM CTAs have to be co-scheduled in one GPC).  fa_debug_set_fwd_split_max changes it (tests).
 std::atomic<int> g_split_cap{4};
 
+// per-device one-time set-up of one instantiation (also what fa_preload_kernels runs ahead of time)
+template <int D, int IS_BF16>
+int configure_fwd_tc() {
+  static DeviceOnce configured;  // the attribute is per device
+  return configured.run([] {
+    FA_CUDA_CHECK(cudaFuncSetAttribute(fwd_tc_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       FwdCfg<D>::kSmemBytes));
+    cudaFuncAttributes attr;  // forces the (lazily loaded) kernel into the context
+    FA_CUDA_CHECK(cudaFuncGetAttributes(&attr, fwd_tc_kernel<D, IS_BF16>));
+    return (int)FA_OK;
+  });
+}
+
 template <int D, int IS_BF16>
 int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUtensorMap &tmV,
                        const FwdParams &p, int B, cudaStream_t stream) {
   using Cfg = FwdCfg<D>;
-  static DeviceOnce configured;  // the attribute is per device
-  int rc = configured.run([] {
-    FA_CUDA_CHECK(cudaFuncSetAttribute(fwd_tc_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::kSmemBytes));
-    return (int)FA_OK;
-  });
+  int rc = configure_fwd_tc<D, IS_BF16>();
   if (rc != FA_OK) return rc;
   FwdParams q = p;
   q.n_blocks = (p.Nq + 2 * kBM - 1) / (2 * kBM);
@@ -688,6 +696,14 @@ int launch_fwd_tc_impl(const CUtensorMap &tmQ, const CUtensorMap &tmK, const CUt
 }
 
 }  // namespace
+
+int preload_fwd_tc() {
+  int rc;
+  if ((rc = configure_fwd_tc<64, 0>()) || (rc = configure_fwd_tc<64, 1>()) || (rc = configure_fwd_tc<128, 0>()) ||
+      (rc = configure_fwd_tc<128, 1>()))
+    return rc;
+  return FA_OK;
+}
 
 void set_fwd_split_max(int cap) { g_split_cap.store(cap < 1 ? 1 : (cap > 8 ? 8 : cap), std::memory_order_relaxed); }
 

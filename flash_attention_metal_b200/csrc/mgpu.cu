@@ -138,6 +138,9 @@ int fa_mgpu_create(void **out, const int *devices, int n_devices) {
     r->transport = FA_RING_TRANSPORT_PEER;
     int rc = ring_init_streams(r);
     if (rc == FA_OK) rc = ring_alloc_flags(r);
+    // nothing may be loaded lazily later: a load synchronises the context, and the context may then hold a
+    // stream parked on a flag that a later rank's enqueue has yet to write
+    if (rc == FA_OK) rc = preload_kernels();
     if (rc != FA_OK) return fail(rc);
   }
   for (int i = 0; i < n_devices; ++i)

@@ -285,6 +285,12 @@ void unmap_peer_windows(Ring *r, void **peers) {
 
 }  // namespace
 
+int preload_ring() {
+  cudaFuncAttributes attr;
+  FA_CUDA_CHECK(cudaFuncGetAttributes(&attr, ring_dkv_add_kernel));
+  return FA_OK;
+}
+
 // ---- ring life cycle (also used by mgpu.cu) ----------------------------------------
 int ring_init_streams(Ring *r) {
   FA_CUDA_CHECK(cudaStreamCreateWithFlags(&r->comm_stream, cudaStreamNonBlocking));

@@ -117,6 +117,19 @@ int flash_attention_backward(const void *Q, const void *K, const void *V, const 
 
 size_t fa_workspace_bytes_backward(int N, int D, int B, int H);
 
+/* Two implementations of the backward, same arguments, same tolerances, both free of float atomics and
+ * bitwise reproducible (process-wide choice; the workspace size covers both):
+ *   FA_BWD_TWO_KERNEL (default)  one kernel owns every dK/dV tile, another every dQ tile; S and dP are
+ *                                recomputed in both (7 GEMM-units for the 5 of the algorithm).
+ *   FA_BWD_FUSED                 one kernel, 5 GEMMs per tile pair; the dQ contributions of the key tiles
+ *                                are added by TMA add-reductions in a fixed (ascending key tile) order
+ *                                enforced with counters in the workspace.  One launch instead of two, less
+ *                                tensor work, but bound by the ordered L2 reduction: measured slower on
+ *                                B200 except for very small problems. */
+enum { FA_BWD_TWO_KERNEL = 0, FA_BWD_FUSED = 1 };
+int fa_set_backward_algorithm(int algorithm);
+int fa_get_backward_algorithm(void);
+
 /* Rectangular (cross-attention) form of flash_attention_v4_half: Nq query rows against Nk
  * keys/values, non-causal, separate strides for Q/O and K/V (the
  * reference only has Nq == Nk).  Ring attention is built on it. */
@@ -253,6 +266,9 @@ void fa_host_release(void);
 const char *fa_last_error(void);
 int fa_version(void);          /* major*10000 + minor*100 + patch */
 int fa_device_count(void);     /* CUDA devices visible; <0 on error */
+/* Loads every 16-bit and ring kernel into the current device's context ahead of time (CUDA loads a kernel
+ * lazily at its first launch, which synchronises the context).  Optional; fa_mgpu_create does it. */
+int fa_preload_kernels(void);
 /* Kernels launched by this library on the calling thread since the last reset
  * (bench.py reports it as gpu_launches). */
 long fa_launch_count(void);

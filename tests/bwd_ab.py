@@ -6,8 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import flash_attention_metal_b200 as fa
 
-setter = fa.lib().fa_debug_set_bwd_mode
-setter.argtypes = [ctypes.c_int]
+setter = lambda two_kernel: fa.set_backward_algorithm(fa.BWD_TWO_KERNEL if two_kernel else fa.BWD_FUSED)
 
 
 def run(B, H, n, d, causal, reps=10):
@@ -35,7 +34,7 @@ def run(B, H, n, d, causal, reps=10):
         torch.cuda.synchronize()
         ts = sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(reps))
         out[mode] = (first, ts[len(ts) // 2], same)
-    setter(0)
+    setter(1)
     flop = 2.5 * 4.0 * B * H * n * n * d * (0.5 if causal else 1.0)
     rel = [((a - b).abs().max() / b.abs().max()).item() for a, b in zip(out[0][0], out[1][0])]
     print(f"B={B} H={H} N={n} d={d} causal={int(causal)}: two-kernel {out[1][1]:.3f} ms ({flop / out[1][1] / 1e9:.0f} TF)  fused {out[0][1]:.3f} ms "

@@ -16,21 +16,17 @@ TOL_REL = {oracle.FP16: 2e-3, oracle.BF16: 1e-2}
 
 @pytest.fixture(scope="module", params=["fused", "two_kernel"])
 def fa(request):
-    """Every test of this file runs on both forms of the backward: the fused five-GEMM kernel
-    (csrc/bwd_fused.cu, the default) and the two-kernel form (csrc/bwd_tc.cu), selected through the
-    library's debug hook."""
-    import ctypes
-
+    """Every test of this file runs on both implementations of the backward: the two-kernel form
+    (csrc/bwd_tc.cu, the default) and the fused five-GEMM kernel (csrc/bwd_fused.cu), selected with
+    fa_set_backward_algorithm."""
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import flash_attention_metal_b200 as fa
 
-    setter = fa.lib().fa_debug_set_bwd_mode
-    setter.argtypes = [ctypes.c_int]
-    setter(1 if request.param == "two_kernel" else 0)
+    fa.set_backward_algorithm(fa.BWD_FUSED if request.param == "fused" else fa.BWD_TWO_KERNEL)
     yield fa
-    setter(0)
+    fa.set_backward_algorithm(fa.BWD_TWO_KERNEL)
 
 
 def dev(x):
