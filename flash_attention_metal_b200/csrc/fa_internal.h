@@ -64,6 +64,13 @@ int preload_kernels();
 // SM count of the current device (cached per device, thread-safe; 148 if the query fails)
 int device_sm_count();
 
+// Restores the caller's current device when an entry point that has to switch devices returns.
+struct DeviceGuard {
+  int saved = -1;
+  DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) { saved = -1; (void)cudaGetLastError(); } }
+  ~DeviceGuard() { if (saved >= 0) (void)cudaSetDevice(saved); }
+};
+
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // fp32 variants (fp32_kernels.cu).  variant: 0 naive, 1 tiled v1, 2 vectorised v2.

@@ -106,6 +106,7 @@ using namespace fa;
 extern "C" {
 
 int fa_mgpu_create(void **out, const int *devices, int n_devices) {
+  DeviceGuard guard;
   FA_REQUIRE(out && devices && n_devices >= 1 && n_devices <= kRingMaxWorld, "bad device list (1..%d devices)", kRingMaxWorld);
   int visible = 0;
   FA_CUDA_CHECK(cudaGetDeviceCount(&visible));
@@ -156,6 +157,7 @@ void *fa_debug_mgpu_ring(void *group, int index) {
 }
 
 int fa_mgpu_destroy(void *group) {
+  DeviceGuard guard;
   group_free(reinterpret_cast<MgpuGroup *>(group));
   return FA_OK;
 }
@@ -171,6 +173,7 @@ fa_stream_t fa_mgpu_stream(void *group, int index) {
 }
 
 int fa_mgpu_synchronize(void *group) {
+  DeviceGuard guard;
   MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
   FA_REQUIRE(g, "null group");
   for (int i = 0; i < g->n; ++i) {
@@ -183,6 +186,7 @@ int fa_mgpu_synchronize(void *group) {
 int fa_mgpu_sharded_forward(void *group, const void *const *Q, const void *const *K, const void *const *V,
                             void *const *O, float *const *L, int N, int D, float scale, int is_causal,
                             const int *heads, int dtype) {
+  DeviceGuard guard;
   MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
   FA_REQUIRE(g && Q && K && V && O && heads, "null argument");
   for (int i = 0; i < g->n; ++i) {
@@ -200,6 +204,7 @@ int fa_mgpu_sharded_backward(void *group, const void *const *Q, const void *cons
                              const void *const *O, const void *const *dO, const float *const *L, float *const *dQ,
                              float *const *dK, float *const *dV, int N, int D, float scale, int is_causal,
                              const int *heads, int dtype) {
+  DeviceGuard guard;
   MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
   FA_REQUIRE(g && Q && K && V && O && dO && L && dQ && dK && dV && heads, "null argument");
   size_t need = 0;
@@ -221,6 +226,7 @@ int fa_mgpu_sharded_backward(void *group, const void *const *Q, const void *cons
 
 int fa_mgpu_ring_forward(void *group, const void *const *Q, const void *const *K, const void *const *V, void *const *O,
                          float *const *L, int n_local, int D, int H, float scale, int is_causal, int dtype) {
+  DeviceGuard guard;
   MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
   FA_REQUIRE(g && Q && K && V && O, "null argument");
   const size_t wsb = fa_ring_workspace_bytes_ex(g->n, FA_RING_TRANSPORT_PEER, n_local, D, H, dtype);
@@ -241,6 +247,7 @@ int fa_mgpu_ring_backward(void *group, const void *const *Q, const void *const *
                           const void *const *O, const void *const *dO, const float *const *L, float *const *dQ,
                           float *const *dK, float *const *dV, int n_local, int D, int H, float scale, int is_causal,
                           int dtype) {
+  DeviceGuard guard;
   MgpuGroup *g = reinterpret_cast<MgpuGroup *>(group);
   FA_REQUIRE(g && Q && K && V && O && dO && L && dQ && dK && dV, "null argument");
   const size_t wsb = fa_ring_workspace_bytes_backward(n_local, D, H, dtype);

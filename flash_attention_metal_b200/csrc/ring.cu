@@ -342,6 +342,7 @@ int ring_ensure_window(Ring *r, size_t bytes) {
 
 void ring_free(Ring *r) {
   if (!r) return;
+  DeviceGuard guard;
   cudaSetDevice(r->device);
   cudaDeviceSynchronize();
   if (!r->group) {
@@ -426,6 +427,7 @@ void fa_debug_set_ring_write_mechanism(int m) { g_write_mech.store(m < 0 ? 0 : (
 int fa_debug_ring_flags(void *ring, uint32_t *out, int n) {
   Ring *r = reinterpret_cast<Ring *>(ring);
   FA_REQUIRE(r && r->flags && out && n > 0 && n <= 1024, "bad arguments");
+  DeviceGuard guard;
   FA_CUDA_CHECK(cudaSetDevice(r->device));
   FA_CUDA_CHECK(cudaMemcpy(out, r->flags, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return FA_OK;
@@ -449,6 +451,7 @@ int fa_ring_create_ex(void **ring_out, const void *unique_id, int rank, int worl
   FA_REQUIRE(transport >= FA_RING_TRANSPORT_AUTO && transport <= FA_RING_TRANSPORT_PEER, "unknown ring transport %d", transport);
   NcclApi *api = nccl();
   if (!api) return set_error(FA_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  DeviceGuard guard;
   FA_CUDA_CHECK(cudaSetDevice(device));
   Ring *r = new Ring();
   r->rank = rank; r->world = world; r->device = device;
@@ -556,6 +559,7 @@ int fa_ring_attention_forward(void *ring, const void *Q, const void *K, const vo
                      r->transport, need, workspace_bytes);
   NcclApi *api = nccl();
   if (P > 1 && r->transport != FA_RING_TRANSPORT_PEER && !api) return set_error(FA_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  DeviceGuard guard;
   FA_CUDA_CHECK(cudaSetDevice(r->device));
   cudaStream_t st = (cudaStream_t)stream_;
   const size_t tile_elems = (size_t)H * n_local * D;
@@ -707,6 +711,7 @@ int fa_ring_attention_backward(void *ring, const void *Q, const void *K, const v
   const bool peer = r->transport == FA_RING_TRANSPORT_PEER && P > 1;
   NcclApi *api = nccl();
   if (P > 1 && !peer && !api) return set_error(FA_ERR_NCCL, "libnccl.so.2 could not be loaded");
+  DeviceGuard guard;
   FA_CUDA_CHECK(cudaSetDevice(r->device));
   cudaStream_t st = (cudaStream_t)stream_, cs = r->comm_stream;
   const size_t tile_elems = (size_t)H * n_local * D;

@@ -48,9 +48,9 @@ def ring_step():
     grp.ring_forward(Q, K, V, O, L, n_local, D, H, scale, a.causal, fa.BF16)
     grp.ring_backward(Q, K, V, O, dO, L, dQ, dK, dV, n_local, D, H, scale, a.causal, fa.BF16)
 ring_step(); grp.synchronize()
-err = max((O[i].float().cpu() - Of[:, rows[i].cuda()].float().cpu()).abs().max().item() for i in range(P))
-errl = max((L[i].cpu() - Lf[:, rows[i].cuda()].cpu()).abs().max().item() for i in range(P))
-berr = [max((x[i].cpu() - y[:, rows[i].cuda()].cpu()).abs().max().item() for i in range(P)) / y.abs().max().item()
+err = max((O[i].float().cpu() - Of[:, rows[i].to(Of.device)].float().cpu()).abs().max().item() for i in range(P))
+errl = max((L[i].cpu() - Lf[:, rows[i].to(Of.device)].cpu()).abs().max().item() for i in range(P))
+berr = [max((x[i].cpu() - y[:, rows[i].to(Of.device)].cpu()).abs().max().item() for i in range(P)) / y.abs().max().item()
         for x, y in ((dQ, gQ), (dK, gK), (dV, gV))]
 if not err <= TOL_O: failures.append(f"ring O max-abs {err}")
 if not errl <= TOL_L: failures.append(f"ring L max-abs {errl}")
