@@ -14,6 +14,8 @@ KEYS = [
     "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum", "lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum",
     "lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum", "launch__registers_per_thread", "launch__grid_size",
     "launch__block_size", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sectors_op_red.sum", "lts__t_bytes.sum.per_second", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
     "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_barrier",
 ]
 
