@@ -34,7 +34,7 @@ EXPORTS = (
     "flash_attention_v4_half_rect", "fa_ring_unique_id_bytes", "fa_ring_get_unique_id", "fa_ring_create",
     "fa_ring_destroy", "fa_ring_workspace_bytes", "fa_ring_attention_forward", "fa_ring_plan", "fa_ring_local_rows",
     "fa_ring_workspace_bytes_backward", "fa_ring_attention_backward", "fa_ring_workspace_bytes_gather",
-    "fa_ring_create_ex", "fa_ring_transport", "fa_ring_workspace_bytes_ex",
+    "fa_ring_create_ex", "fa_ring_transport", "fa_ring_workspace_bytes_ex", "fa_ring_merge_plan",
     "flash_attention_backward_rect", "fa_rowsum_delta",
     "fa_mgpu_create", "fa_mgpu_destroy", "fa_mgpu_device_count", "fa_mgpu_stream", "fa_mgpu_synchronize",
     "fa_mgpu_sharded_forward", "fa_mgpu_sharded_backward", "fa_mgpu_ring_forward", "fa_mgpu_ring_backward",
@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
         ip = C.POINTER(i32)
         L.fa_ring_plan.argtypes = [i32, i32, i32, i32, i32, ip, ip, ip, ip, ip, ip]
         L.fa_ring_local_rows.argtypes = [i32, i32, i32, i32, C.POINTER(i64), ip]
+        L.fa_ring_merge_plan.argtypes = [i32, i32, i32, i32, i32, ip, ip, ip]
         _lib = L
     return _lib
 
@@ -279,6 +280,13 @@ def ring_plan(rank, world, step, n_local, is_causal):
     """(src_rank, q_off, q_rows, k_off, k_rows, block_causal) of the block `rank` computes at `step`."""
     out = [C.c_int() for _ in range(6)]
     _check(lib().fa_ring_plan(rank, world, step, n_local, int(is_causal), *[C.byref(o) for o in out]))
+    return tuple(o.value for o in out)
+
+
+def ring_merge_plan(rank, world, step, n_local, is_causal):
+    """(lo, hi, half_rows): merge modes (0 only partial, 1 first, 2 middle, 3 last) of the step's forward launch."""
+    out = [C.c_int() for _ in range(3)]
+    _check(lib().fa_ring_merge_plan(rank, world, step, n_local, int(is_causal), *[C.byref(o) for o in out]))
     return tuple(o.value for o in out)
 
 

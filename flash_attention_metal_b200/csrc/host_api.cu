@@ -1,7 +1,7 @@
 // Host-buffer entry points (fa_host_*): the one-call form for a caller whose tensors live
 // in host memory, as the reference's do (MTLResourceStorageModeShared, main.mm:104-115).
 //
-// Device scratch comes from a process-wide grow-only pool (released by fa_host_release), so
+// Device scratch comes from a grow-only pool per device (released by fa_host_release), so
 // repeated calls do not pay cudaMalloc.  The 16-bit calls are pipelined over groups of heads
 // on three streams -- host->device copies of group g+1, kernels of group g and device->host
 // copies of group g-1 overlap -- because heads are independent (kernels.metal:622).  Pass
@@ -23,16 +23,10 @@ struct HostPool {
   cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
   static constexpr int kMaxGroups = 64;
   cudaEvent_t in_done[kMaxGroups] = {}, run_done[kMaxGroups] = {};
-  int device = -1;
   std::mutex mu;
 
-  int ensure_device() {
-    int dev = 0;
-    FA_CUDA_CHECK(cudaGetDevice(&dev));
-    if (device != dev) {
-      release();
-      device = dev;
-    }
+  // streams and events are created on first use, on the pool's own device (the caller's current device)
+  int ensure_streams() {
     if (!s_in) {
       FA_CUDA_CHECK(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
       FA_CUDA_CHECK(cudaStreamCreateWithFlags(&s_run, cudaStreamNonBlocking));
@@ -69,7 +63,25 @@ struct HostPool {
   }
 };
 
-HostPool g_pool;
+// One pool per device: a process that drives several GPUs (one host thread per GPU, or one thread switching
+// devices) keeps every device's scratch and streams; calls on different devices do not serialise on one lock.
+constexpr int kMaxDevices = 64;
+HostPool g_pools[kMaxDevices];
+
+int current_pool(HostPool **out) {
+  int dev = 0;
+  FA_CUDA_CHECK(cudaGetDevice(&dev));
+  FA_REQUIRE(dev >= 0 && dev < kMaxDevices, "device index %d out of range", dev);
+  *out = &g_pools[dev];
+  return FA_OK;
+}
+
+// error path after something has been enqueued: do not return while copies may still touch the caller's buffers
+int fail_after_enqueue(HostPool &pool, int rc) {
+  if (pool.s_in) { cudaStreamSynchronize(pool.s_in); cudaStreamSynchronize(pool.s_run); cudaStreamSynchronize(pool.s_out); }
+  (void)cudaGetLastError();
+  return rc;
+}
 
 // fp32 -> 16-bit (round to nearest even), 8 elements per thread: the optional 16-bit gradient output of
 // the host-buffer call (halves the device->host bytes, which bound that call)
@@ -96,8 +108,12 @@ int host_half_impl(const void *Q, const void *K, const void *V, const void *dO, 
   FA_REQUIRE(Q && K && V && O && N >= 1 && B >= 1 && H >= 1, "bad arguments");
   FA_REQUIRE(D == 64 || D == 128, "D must be 64 or 128 (got %d)", D);
   FA_REQUIRE(!bwd || (dQ && dK && dV), "backward needs dQ, dK and dV");
+  HostPool *pool_ptr = nullptr;
+  int rc = current_pool(&pool_ptr);
+  if (rc != FA_OK) return rc;
+  HostPool &g_pool = *pool_ptr;
   std::lock_guard<std::mutex> lock(g_pool.mu);
-  int rc = g_pool.ensure_device();
+  rc = g_pool.ensure_streams();
   if (rc != FA_OK) return rc;
   const int heads = B * H;
   const size_t head_elems = (size_t)N * D;
@@ -144,6 +160,9 @@ int host_half_impl(const void *Q, const void *K, const void *V, const void *dO, 
   }
   auto at = [](const void *p, size_t off) { return (const void *)((const char *)p + off); };
   auto atw = [](void *p, size_t off) { return (void *)((char *)p + off); };
+  // everything below only enqueues; on any failure the streams are drained before the error is returned, so
+  // that no copy still touches the caller's buffers after the call
+  auto enqueue_all = [&]() -> int {
   for (int g = 0; g < groups; ++g) {
     const int h0 = group_h0[g], nh = group_nh[g];
     const size_t ob = (size_t)h0 * hb, of = (size_t)h0 * hf, ol = (size_t)h0 * hl;
@@ -190,6 +209,10 @@ int host_half_impl(const void *Q, const void *K, const void *V, const void *dO, 
       FA_CUDA_CHECK(cudaMemcpyAsync(atw(dV, of), at(gV, of), nh * hf, cudaMemcpyDeviceToHost, g_pool.s_out));
     }
   }
+  return FA_OK;
+  };
+  rc = enqueue_all();
+  if (rc != FA_OK) return fail_after_enqueue(g_pool, rc);
   FA_CUDA_CHECK(cudaStreamSynchronize(g_pool.s_out));
   FA_CUDA_CHECK(cudaStreamSynchronize(g_pool.s_run));
   return FA_OK;
@@ -206,8 +229,12 @@ int fa_host_attention_f32(int variant, const float *Q, const float *K, const flo
                           int N, int D, float scale, int is_causal) {
   FA_REQUIRE(variant >= 0 && variant <= 2, "variant must be 0, 1 or 2");
   FA_REQUIRE(Q && K && V && O && N >= 1 && D >= 1, "bad arguments");
+  HostPool *pool_ptr = nullptr;
+  int rc = current_pool(&pool_ptr);
+  if (rc != FA_OK) return rc;
+  HostPool &g_pool = *pool_ptr;
   std::lock_guard<std::mutex> lock(g_pool.mu);
-  int rc = g_pool.ensure_device();
+  rc = g_pool.ensure_streams();
   if (rc != FA_OK) return rc;
   const size_t bytes = (size_t)N * D * sizeof(float);
   void *q, *k, *v, *o;
@@ -215,13 +242,18 @@ int fa_host_attention_f32(int variant, const float *Q, const float *K, const flo
       (rc = g_pool.get(3, bytes, &o)))
     return rc;
   cudaStream_t st = g_pool.s_run;
-  FA_CUDA_CHECK(cudaMemcpyAsync(q, Q, bytes, cudaMemcpyHostToDevice, st));
-  FA_CUDA_CHECK(cudaMemcpyAsync(k, K, bytes, cudaMemcpyHostToDevice, st));
-  FA_CUDA_CHECK(cudaMemcpyAsync(v, V, bytes, cudaMemcpyHostToDevice, st));
-  rc = launch_fp32(variant, (const float *)q, (const float *)k, (const float *)v, (float *)o, N, D, scale, 0, 0,
-                   is_causal, 1, 1, st);
-  if (rc != FA_OK) return rc;
-  FA_CUDA_CHECK(cudaMemcpyAsync(O, o, bytes, cudaMemcpyDeviceToHost, st));
+  auto enqueue_all = [&]() -> int {
+    FA_CUDA_CHECK(cudaMemcpyAsync(q, Q, bytes, cudaMemcpyHostToDevice, st));
+    FA_CUDA_CHECK(cudaMemcpyAsync(k, K, bytes, cudaMemcpyHostToDevice, st));
+    FA_CUDA_CHECK(cudaMemcpyAsync(v, V, bytes, cudaMemcpyHostToDevice, st));
+    const int lrc = launch_fp32(variant, (const float *)q, (const float *)k, (const float *)v, (float *)o, N, D, scale, 0, 0,
+                                is_causal, 1, 1, st);
+    if (lrc != FA_OK) return lrc;
+    FA_CUDA_CHECK(cudaMemcpyAsync(O, o, bytes, cudaMemcpyDeviceToHost, st));
+    return FA_OK;
+  };
+  rc = enqueue_all();
+  if (rc != FA_OK) return fail_after_enqueue(g_pool, rc);
   FA_CUDA_CHECK(cudaStreamSynchronize(st));
   return FA_OK;
 }
@@ -249,8 +281,14 @@ int fa_host_attention_fwd_bwd_half_ex(const void *Q, const void *K, const void *
 }
 
 void fa_host_release(void) {
-  std::lock_guard<std::mutex> lock(g_pool.mu);
-  g_pool.release();
+  DeviceGuard guard;
+  for (int dev = 0; dev < kMaxDevices; ++dev) {
+    HostPool &pool = g_pools[dev];
+    std::lock_guard<std::mutex> lock(pool.mu);
+    if (!pool.s_in && !pool.ptr[0]) continue;
+    if (cudaSetDevice(dev) != cudaSuccess) { (void)cudaGetLastError(); continue; }
+    pool.release();
+  }
 }
 
 }  // extern "C"

@@ -220,6 +220,22 @@ int merge_mode(bool first, bool last) {
   return first ? (last ? 0 : 1) : (last ? 3 : 2);  // kMergeNone / First / Last / Middle (fwd_tc.cu)
 }
 
+// How the forward launch of ring step `step` folds its partial into the running (O, L) pair (pure host logic,
+// exported as fa_ring_merge_plan and tested on CPU): merge modes for the rows of the launch below / from
+// `half_rows`.  Not causal: every local row takes part in every step.  Causal (zig-zag): the first chunk (local
+// rows < c) takes part in steps 0 .. rank, the second chunk in every step; a launch that covers only the second
+// chunk (K/V from a higher rank) has one row range.
+void merge_plan(int rank, int world, int step, int n_local, int is_causal, int q_off, int *lo, int *hi, int *half_rows) {
+  if (!is_causal) {
+    *lo = *hi = merge_mode(step == 0, step == world - 1);
+    *half_rows = 0;
+    return;
+  }
+  const int first_chunk = merge_mode(step == 0, step == rank), second_chunk = merge_mode(step == 0, step == world - 1);
+  if (q_off == 0) { *lo = first_chunk; *hi = second_chunk; *half_rows = n_local / 2; }
+  else { *lo = *hi = second_chunk; *half_rows = 0; }
+}
+
 
 struct IpcBlob {  // what ranks exchange about a window (padded to 128 bytes)
   cudaIpcMemHandle_t handle;
@@ -514,6 +530,17 @@ int fa_ring_plan(int rank, int world, int step, int n_local, int is_causal, int 
   return FA_OK;
 }
 
+// Merge modes of the forward launch of a ring step (0 none, 1 first, 2 middle, 3 last) for its rows below /
+// from half_rows (row indices relative to the launch's first query row).  Host-only.
+int fa_ring_merge_plan(int rank, int world, int step, int n_local, int is_causal, int *lo, int *hi, int *half_rows) {
+  Block b;
+  if (!lo || !hi || !half_rows || ring_plan(rank, world, step, n_local, is_causal, &b) != 0)
+    return set_error(FA_ERR_INVALID, "bad ring plan arguments (rank %d world %d step %d n_local %d causal %d)", rank,
+                     world, step, n_local, is_causal);
+  merge_plan(rank, world, step, n_local, is_causal, b.q_off, lo, hi, half_rows);
+  return FA_OK;
+}
+
 // Global row index of the first row of each local chunk (chunk 1 has 0 rows when not causal).
 int fa_ring_local_rows(int rank, int world, int n_local, int is_causal, int64_t first_row[2], int rows[2]) {
   FA_REQUIRE(world >= 1 && rank >= 0 && rank < world && n_local >= 1, "bad arguments");
@@ -573,7 +600,6 @@ int fa_ring_attention_forward(void *ring, const void *Q, const void *K, const vo
   float *l_acc = reinterpret_cast<float *>(ws + kv_area + tile_elems * 4);
   const int next = (r->rank + 1) % P, prev = (r->rank - 1 + P) % P;
   const int64_t hs = (int64_t)n_local * D;
-  const int c = n_local / 2;
 
   // ---- local work of ring step s on the chunk (curK, curV) of rank (rank - s) mod P: ONE launch,
   //      the running (O, L) is folded in the kernel epilogue ----
@@ -586,15 +612,7 @@ int fa_ring_attention_forward(void *ring, const void *Q, const void *K, const vo
     FwdMerge m;
     m.O_acc = o_acc + (int64_t)b.q_off * D;
     m.L_acc = l_acc + b.q_off;
-    if (!is_causal) {
-      m.lo = m.hi = merge_mode(s == 0, s == P - 1);
-      m.half_rows = 0;
-    } else {
-      // first zig-zag chunk (local rows < c): touched at steps 0..rank; second chunk: at every step
-      const int lo = merge_mode(s == 0, s == r->rank), hi = merge_mode(s == 0, s == P - 1);
-      if (b.q_off == 0) { m.lo = lo; m.hi = hi; m.half_rows = c; }
-      else { m.lo = m.hi = hi; m.half_rows = 0; }
-    }
+    merge_plan(r->rank, P, s, n_local, is_causal, b.q_off, &m.lo, &m.hi, &m.half_rows);
     return launch_fwd_tc_rect(q, k, v, reinterpret_cast<uint16_t *>(O) + (int64_t)b.q_off * D,
                               L_out ? L_out + b.q_off : nullptr, b.q_rows, b.k_rows, D, scale, (int64_t)H * hs, hs,
                               (int64_t)H * hs, hs, b.causal, 1, H, dtype, st, &m);

@@ -207,6 +207,9 @@ int fa_ring_attention_backward(fa_ring_t ring, const void *Q, const void *K, con
 int fa_ring_plan(int rank, int world, int step, int n_local, int is_causal, int *src_rank, int *q_off,
                  int *q_rows, int *k_off, int *k_rows, int *block_causal);
 int fa_ring_local_rows(int rank, int world, int n_local, int is_causal, int64_t first_row[2], int rows[2]);
+/* how the forward launch of a step folds its partial result into the running (O, L): merge mode (0 the only
+ * partial, 1 first, 2 middle, 3 last) of the launch's rows below / from half_rows */
+int fa_ring_merge_plan(int rank, int world, int step, int n_local, int is_causal, int *lo, int *hi, int *half_rows);
 
 /* ---- fa_mgpu_*: ONE process driving several GPUs of one box (the reference's
  * harness is a single process, main.mm:881-1204).  The group owns a stream per device, its scratch

@@ -204,6 +204,25 @@ def test_host_buffer_fwd_bwd_entry_point(fa):
     fa.host_release()
 
 
+@pytest.mark.parametrize("gdt", [oracle.BF16, oracle.FP16])
+def test_host_buffer_call_with_16_bit_gradients(fa, gdt):
+    """fa_host_attention_fwd_bwd_half_ex with grad_dtype: the gradients leave the device rounded to 16 bits
+    (round to nearest even) -- bit for bit the fp32 gradients of the ordinary call, rounded."""
+    B, H, n, d, dtype = 1, 3, 384, 64, oracle.BF16
+    bits = make_bits(n, d, dtype, heads=(B, H), seeds=(21, 22, 23, 24))
+    o = np.empty((B, H, n, d), np.uint16)
+    l = np.empty((B, H, n), np.float32)
+    g32 = [np.empty((B, H, n, d), np.float32) for _ in range(3)]
+    fa.host_attention_fwd_bwd_half(bits[0], bits[1], bits[2], bits[3], o, l, *g32, n, d, 0.125, True, B, H, dtype)
+    g16 = [np.zeros((B, H, n, d), np.uint16) for _ in range(3)]
+    o2 = np.empty_like(o)
+    fa.host_attention_fwd_bwd_half_ex(bits[0], bits[1], bits[2], bits[3], o2, l, *g16, n, d, 0.125, True, B, H, dtype, gdt)
+    assert np.array_equal(o, o2)
+    for a, b in zip(g16, g32):
+        assert np.array_equal(a, oracle.to_half_bits(b, gdt))
+    fa.host_release()
+
+
 def test_no_writes_outside_the_output_tensors(fa):
     """compute-sanitizer is closed on this pool, so bounds are checked with guard bands: every output
     sits inside a larger buffer filled with a sentinel, N is ragged (not a multiple of any tile), and

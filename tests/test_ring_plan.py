@@ -162,3 +162,51 @@ def test_two_process_gloo_ring(fa, causal):
         p.join(120)
         assert p.exitcode == 0
     assert max(ret.values()) < 2e-6
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("causal", [False, True])
+def test_merge_plan_gives_every_row_range_one_first_and_one_last(fa, world, causal):
+    """fa_ring_merge_plan (the function the ring driver asks how a step's launch folds its partial into the running
+    (O, L) inside the kernel epilogue): over the steps of a call every local row must be written exactly as
+    'the only partial' once, or as first, middle ..., last in that order -- and rows a step's block does not
+    cover must not be touched by it."""
+    n_local = 64
+    for rank in range(world):
+        state = np.zeros(n_local, dtype=np.int64)  # 0 untouched, 1 running pair started, 2 finished
+        for step in range(world):
+            src, q_off, q_rows, k_off, k_rows, bc = fa.ring_plan(rank, world, step, n_local, causal)
+            lo, hi, half = fa.ring_merge_plan(rank, world, step, n_local, causal)
+            for r in range(q_rows):
+                mode = lo if r < half else hi
+                row = q_off + r
+                if mode == 0:      # the only partial of this row
+                    assert state[row] == 0
+                    state[row] = 2
+                elif mode == 1:    # first: starts the running pair
+                    assert state[row] == 0
+                    state[row] = 1
+                elif mode == 2:    # middle: needs a running pair, leaves one
+                    assert state[row] == 1
+                else:              # last: needs a running pair, writes the final O and L
+                    assert mode == 3 and state[row] == 1
+                    state[row] = 2
+        assert (state == 2).all(), (rank, state)
+
+
+def test_ring_api_argument_errors_without_gpu(fa):
+    with pytest.raises(fa.FlashAttnError, match="bad ring plan"):
+        fa.ring_merge_plan(2, 2, 0, 64, True)
+    with pytest.raises(fa.FlashAttnError, match="bad ring plan"):
+        fa.ring_plan(0, 2, 0, 63, True)  # causal needs an even n_local
+    with pytest.raises(fa.FlashAttnError, match="unknown backward algorithm"):
+        fa.set_backward_algorithm(7)
+    assert fa.get_backward_algorithm() == fa.BWD_TWO_KERNEL
+    L = fa.lib()
+    # forward workspace: the all-gather transport needs room for every rank's K/V, the others two slots
+    small = L.fa_ring_workspace_bytes_ex(8, fa.TRANSPORT_PEER, 1024, 128, 4, fa.BF16)
+    assert small == L.fa_ring_workspace_bytes_ex(8, fa.TRANSPORT_NCCL, 1024, 128, 4, fa.BF16) == L.fa_ring_workspace_bytes(1024, 128, 4, fa.BF16)
+    assert L.fa_ring_workspace_bytes_ex(8, fa.TRANSPORT_NCCL_GATHER, 1024, 128, 4, fa.BF16) == small + 6 * 2 * (4 * 1024 * 128 * 2)
+    assert L.fa_ring_workspace_bytes_backward(1024, 128, 4, fa.BF16) > small
+    # the backward workspace covers the fused kernel's ordering counters and delta
+    assert fa.workspace_bytes_backward(1000, 128, 2, 3) >= 2 * 3 * 1000 * 4 + 2 * 3 * 8 * 4
