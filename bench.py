@@ -407,7 +407,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+
+        # a rank that fails must not leave the others waiting in a collective for NCCL's default 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     fa.lib()
     scale = float(D ** -0.5)
     st = torch.cuda.current_stream()

@@ -77,3 +77,18 @@ def test_tflops_plot_script_reads_the_same_csv(tmp_path):
     ten.write_text("\n".join(",".join(l.split(",")[:10]) for l in lines) + "\n")
     subprocess.check_call([sys.executable, script, str(ten), "-o", str(out)], stdout=subprocess.DEVNULL)
     assert out.read_text().count("<polyline") >= 3
+
+
+def test_harness_config_1_reproduces_the_reference_cpu_anchors():
+    """`flash_attn --config 1` (BASELINE config 1: the reference's CPU verifier alone, N=128, main.mm:128-159 loop
+    order) needs no GPU; its output carries the known-answer values of SURVEY.md section 8c."""
+    exe = os.path.join(ROOT, "harness", "flash_attn")
+    if not os.path.exists(exe):
+        import pytest
+
+        pytest.skip("harness not built")
+    out = subprocess.run([exe, "--config", "1"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr[-500:]
+    m = re.search(r"O\[0\] = (-?[0-9.e+-]+), sum\(O\) = (-?[0-9.e+-]+)", out.stdout)
+    assert m, out.stdout
+    assert abs(float(m.group(1)) - (-0.0598809421)) < 1e-6 and abs(float(m.group(2)) - 0.307174703) < 1e-4
