@@ -31,8 +31,7 @@ namespace fa { long long *g_trace_buffer = nullptr; }
 namespace fa {
 static std::atomic<int> g_bwd_mode{0};
 int bwd_mode() { return g_bwd_mode.load(std::memory_order_relaxed); }
-static std::atomic<int> g_dkdv_warps{8};
-int dkdv_warps() { return g_dkdv_warps.load(std::memory_order_relaxed); }
+
 static std::atomic<int> g_l2_group_mb{48};
 int l2_group_mb() { return g_l2_group_mb.load(std::memory_order_relaxed); }
 
@@ -88,10 +87,6 @@ int fa_set_backward_algorithm(int algorithm) {
   return FA_OK;
 }
 int fa_get_backward_algorithm(void) { return g_bwd_mode.load(std::memory_order_relaxed); }
-
-// Development aid (not in the public header): 16 selects the dK/dV kernel with sixteen element-wise warps
-// (bwd_dkdv16_kernel, csrc/bwd_tc.cu), 8 the default kernel.
-void fa_debug_set_dkdv_warps(int warps) { g_dkdv_warps.store(warps == 16 ? 16 : 8, std::memory_order_relaxed); }
 
 // Development aid (not in the public header): L2 budget of a dispatch group of heads, in MB.
 void fa_debug_set_l2_group_mb(int mb) { g_l2_group_mb.store(mb < 0 ? 0 : mb, std::memory_order_relaxed); }

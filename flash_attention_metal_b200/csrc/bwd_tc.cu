@@ -57,23 +57,6 @@ constexpr float kLog2e = 1.4426950408889634f;
 #ifndef FA_BWD_SPLIT
 #define FA_BWD_SPLIT 1
 #endif
-// Tuning knobs of the dK/dV kernel's element-wise loop (A/B-ed on B200, tests/bwd_ab.py):
-//   FA_DKDV_LATE_BAR  the warpgroup barrier that publishes the per-column statistics is taken after the
-//                     wait for S^T instead of before it (two idle periods overlap instead of adding up)
-//   FA_DKDV_Y_AHEAD   both halves of dP^T are loaded from TMEM before phase 2 computes (one exposed TMEM
-//                     round trip per tile instead of two)
-//   FA_BWD_REGS_WIDE  registers of the element-wise warps after setmaxnreg (the other warpgroup gets the rest
-//                     of 12 x 168: 216 -> 72, 208 -> 88)
-#ifndef FA_DKDV_LATE_BAR
-#define FA_DKDV_LATE_BAR 0
-#endif
-#ifndef FA_DKDV_Y_AHEAD
-#define FA_DKDV_Y_AHEAD 0
-#endif
-#ifndef FA_BWD_REGS_WIDE
-#define FA_BWD_REGS_WIDE 216
-#endif
-constexpr int kBwdRegsWide = FA_BWD_REGS_WIDE, kBwdRegsNarrow = FA_BWD_REGS_WIDE == 216 ? 64 : (2016 - 8 * FA_BWD_REGS_WIDE) / 4;
 constexpr int kBwdEmu = FA_BWD_EMU;
 constexpr int kDkdvParts = FA_BWD_SPLIT ? 2 : 1;  // hand-offs per phase in bwd_dkdv_kernel
 constexpr int kDqParts = FA_BWD_SPLIT ? 4 : 1;    // dS hand-offs per item in bwd_dq_kernel
@@ -257,7 +240,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp < 8) {
     // ======================= element-wise warpgroups =======================
-    setmaxnreg_inc<kBwdRegsWide>();
+    setmaxnreg_inc<216>();
     const int wg = warp >> 2;
     const int tid = (warp & 3) * 32 + lane;  // TMEM lane = key row within the tile
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
@@ -295,12 +278,11 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ld[tid] = stat_next * stat_coef;
       FA_PCLK(cb);
       stat_next = fetch_stat(i + 1);
-      if (!FA_DKDV_LATE_BAR) named_bar_sync(1 + wg, 128);
+      named_bar_sync(1 + wg, 128);
       FA_PDO(t_top += cb - ca; t_top2 += clock64() - cb);
       // ---- phase 1: P^T = exp2(S^T * c - L * log2e) ----
       FA_PCLK(c0);
       mbar_wait(x_full, i & 1);
-      if (FA_DKDV_LATE_BAR) named_bar_sync(1 + wg, 128);
       FA_PCLK(c1);
       tc_fence_after();
       uint32_t pr[2][32];  // S^T, then P^T (fp32 bits), kept for phase 2
@@ -353,20 +335,11 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_wait(y_full, i & 1);
       FA_PCLK(c3);
       tc_fence_after();
-      uint32_t yy[2][32];
-      if (FA_DKDV_Y_AHEAD) {
-        tmem_ld32(tY, yy[0]);
-        tmem_ld32(tY + 32, yy[1]);
-        tmem_wait_ld();
-      }
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
-        uint32_t dk[16];
-        uint32_t (&y)[32] = yy[c];
-        if (!FA_DKDV_Y_AHEAD) {
-          tmem_ld32(tY + c * 32, y);
-          tmem_wait_ld();
-        }
+        uint32_t y[32], dk[16];
+        tmem_ld32(tY + c * 32, y);
+        tmem_wait_ld();
 #pragma unroll
         for (int e = 0; e < 32; e += 4) {
           uint64_t da, db;  // -D*scale of four consecutive query columns
@@ -414,7 +387,7 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else {
-    setmaxnreg_dec<kBwdRegsNarrow>();
+    setmaxnreg_dec<64>();
     if (warp == kLoadWarp) {
       // ============================ TMA producer ============================
       if (elect_one()) {
@@ -523,271 +496,6 @@ bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------
-// 2b. dK / dV with SIXTEEN element-wise warps (640 threads): the same kernel as above, but each
-//     warpgroup of the element-wise side owns 32 query columns instead of 64 (quad q4 = half * 2 + c:
-//     query columns [64 half + 32 c, +32)), so that four warps per scheduler instead of two hide the
-//     TMEM / MUFU / shared-memory latencies of the two phases.  Built for D = 64, where the ncu capture
-//     shows the tensor pipe 38 % active behind the element-wise chain; selected
-//     with fa_debug_set_dkdv_warps(16).  Differences to the 8-warp form: a thread's 16-bit P^T / dS^T go
-//     over the first 16 columns of ITS OWN 32-column chunk (no other warp reads them), so k-step kk of the
-//     accumulating MMAs reads columns (kk >> 2) * 64 + ((kk & 3) >> 1) * 32 + (kk & 1) * 8; the statistics
-//     barrier spans the 256 threads of a 64-column half; registers 104 / 64 (16 x 104 + 4 x 64 = 20 x 96).
-// ---------------------------------------------------------------------------
-constexpr int kDkdv16Threads = 640;
-constexpr int kDkdv16MmaWarp = 16, kDkdv16LoadWarp = 17;
-
-template <int D, int IS_BF16>
-__global__ void __launch_bounds__(kDkdv16Threads, 1)
-bwd_dkdv16_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmdO,
-                  const BwdParams p) {
-  using Cfg = DkdvCfg<D>;
-  extern __shared__ unsigned char smem_raw[];
-  unsigned char *smem = reinterpret_cast<unsigned char *>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  if (smem - smem_raw > 512) __trap();
-  unsigned char *sK = smem;
-  unsigned char *sV = smem + Cfg::kTile;
-  unsigned char *sQ = smem + 2 * Cfg::kTile;                      // [kQSlots]
-  unsigned char *sDO = sQ + Cfg::kQSlots * Cfg::kTile;            // [kDoSlots]
-  float *sLD = reinterpret_cast<float *>(smem + Cfg::kSmemTiles);
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + Cfg::kSmemTiles + Cfg::kStatBytes);
-  uint64_t *res_full = bars, *acc_full = bars + 1, *x_full = bars + 2, *y_full = bars + 3;
-  uint64_t *p_ready = bars + 4;     // [2] P^T chunk c stored by the two quads that own a chunk c
-  uint64_t *ds_ready = bars + 6;    // [2]
-  uint64_t *q_full = bars + 8;
-  uint64_t *q_empty = q_full + Cfg::kQSlots;
-  uint64_t *do_full = q_empty + Cfg::kQSlots;
-  uint64_t *do_empty = do_full + Cfg::kDoSlots;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(do_empty + Cfg::kDoSlots);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const BlockCoord bc = decode_block(p.group, p.n_heads, p.H);
-  if (bc.b < 0) return;
-  const int j = bc.blk, h = bc.h, b = bc.b;
-  const int key0 = j * 128;
-  const int n_tiles_all = (p.Nq + 127) / 128;
-  const int i_start = p.causal ? j : 0;
-  const int n = n_tiles_all - i_start;
-  const int64_t kv_off = (int64_t)b * p.kv_batch_stride + (int64_t)h * p.kv_head_stride;
-  const int64_t vec_off = ((int64_t)b * p.batch_stride + (int64_t)h * p.head_stride) / D;
-
-  if (threadIdx.x == 0) {
-    mbar_init(res_full, 1);
-    mbar_init(acc_full, 1);
-    mbar_init(x_full, 1);
-    mbar_init(y_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&p_ready[i], 8 * kArrivalsPerWarp); mbar_init(&ds_ready[i], 8 * kArrivalsPerWarp); }
-    for (int i = 0; i < Cfg::kQSlots; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    for (int i = 0; i < Cfg::kDoSlots; ++i) { mbar_init(&do_full[i], 1); mbar_init(&do_empty[i], 1); }
-    fence_barrier_init();
-  }
-  if (warp == kDkdv16MmaWarp) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 16) {
-    // ======================= element-wise quads =======================
-    setmaxnreg_inc<104>();
-    const int q4 = warp >> 2, half = q4 >> 1, c = q4 & 1;
-    const int tid = (warp & 3) * 32 + lane;  // TMEM lane = key row within the tile
-    const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-    const uint32_t tX = tmem_base + lane_off + half * 64 + c * 32;         // my 32 columns of S^T / P^T
-    const uint32_t tY = tmem_base + lane_off + 128 + half * 64 + c * 32;   // ... of dP^T / dS^T
-    const int key = key0 + tid;
-    // statistics of the 64 query columns of this half: written by the c == 0 quad (threads 0-63: -L log2e,
-    // 64-127: -D scale), read by both quads of the half
-    const float *stat_src = (tid < 64 ? p.L : p.delta) + vec_off + half * 64 + (tid & 63);
-    const float stat_coef = tid < 64 ? -kLog2e : -p.scale;
-    auto fetch_stat = [&](int i) -> float {
-      const int q_first = (i_start + i) * 128;
-      float v = tid < 64 ? CUDART_INF_F : 0.f;
-      if (c == 0 && i < n && q_first + half * 64 + (tid & 63) < p.Nq) v = __ldg(stat_src + q_first);
-      return v;
-    };
-    float stat_next = fetch_stat(0);
-    const uint64_t scale_log2_2 = pack_f32x2(p.scale_log2, p.scale_log2), scale_2 = pack_f32x2(p.scale, p.scale);
-    for (int i = 0; i < n; ++i) {
-      const int q0 = (i_start + i) * 128 + half * 64 + c * 32;  // first query column of my chunk
-      float *ld = sLD + (half * 2 + (i & 1)) * 128;
-      if (c == 0) ld[tid] = stat_next * stat_coef;
-      stat_next = fetch_stat(i + 1);
-      named_bar_sync(1 + half, 256);
-      // ---- phase 1: P^T = exp2(S^T * c - L * log2e) ----
-      mbar_wait(x_full, i & 1);
-      tc_fence_after();
-      uint32_t pr[32];  // S^T, then P^T (fp32 bits), kept for phase 2
-      tmem_ld32(tX, pr);
-      tmem_wait_ld();
-      const bool diag = p.causal && (q0 < key0 + 128);
-      const uint32_t ld_s = smem_u32(ld) + c * 32 * 4;
-      {
-        uint32_t pk[16];
-        if (!diag) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            uint64_t la, lb;
-            lds_v2b64(ld_s + e * 4, la, lb);
-            const uint64_t xa = fma_f32x2(pack_u32x2(pr[e], pr[e + 1]), scale_log2_2, la);
-            const uint64_t xb = fma_f32x2(pack_u32x2(pr[e + 2], pr[e + 3]), scale_log2_2, lb);
-            const uint64_t pa = exp2_pair(xa, emulate_pair(e >> 1)), pb = exp2_pair(xb, emulate_pair((e >> 1) + 1));
-            pr[e] = __float_as_uint(lo_f32(pa)); pr[e + 1] = __float_as_uint(hi_f32(pa));
-            pr[e + 2] = __float_as_uint(lo_f32(pb)); pr[e + 3] = __float_as_uint(hi_f32(pb));
-            pk[e >> 1] = pack2<IS_BF16>(lo_f32(pa), hi_f32(pa));
-            pk[(e >> 1) + 1] = pack2<IS_BF16>(lo_f32(pb), hi_f32(pb));
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            uint64_t la, lb;
-            lds_v2b64(ld_s + (e & ~3) * 4, la, lb);
-            const uint64_t x2 = fma_f32x2(pack_u32x2(pr[e], pr[e + 1]), scale_log2_2, (e & 2) ? lb : la);
-            float p0 = ex2(lo_f32(x2)), p1 = ex2(hi_f32(x2));
-            if (key > q0 + e) p0 = 0.f;
-            if (key > q0 + e + 1) p1 = 0.f;
-            pr[e] = __float_as_uint(p0);
-            pr[e + 1] = __float_as_uint(p1);
-            pk[e >> 1] = pack2<IS_BF16>(p0, p1);
-          }
-        }
-        tmem_st16(tX, pk);  // over the first 16 columns of my own chunk
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive_warp(&p_ready[c]);
-      }
-      // ---- phase 2: dS^T = P^T o (dP^T * scale - D * scale) ----
-      mbar_wait(y_full, i & 1);
-      tc_fence_after();
-      {
-        uint32_t y[32], dk[16];
-        tmem_ld32(tY, y);
-        tmem_wait_ld();
-#pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-          uint64_t da, db;
-          lds_v2b64(ld_s + (64 + e) * 4, da, db);
-          const uint64_t ga = fma_f32x2(pack_u32x2(y[e], y[e + 1]), scale_2, da);
-          const uint64_t gb = fma_f32x2(pack_u32x2(y[e + 2], y[e + 3]), scale_2, db);
-          const uint64_t d2a = mul_f32x2(pack_u32x2(pr[e], pr[e + 1]), ga);
-          const uint64_t d2b = mul_f32x2(pack_u32x2(pr[e + 2], pr[e + 3]), gb);
-          dk[e >> 1] = pack2<IS_BF16>(lo_f32(d2a), hi_f32(d2a));
-          dk[(e >> 1) + 1] = pack2<IS_BF16>(lo_f32(d2b), hi_f32(d2b));
-        }
-        tmem_st16(tY, dk);
-        tmem_wait_st();
-        tc_fence_before();
-        mbar_arrive_warp(&ds_ready[c]);
-      }
-    }
-    // ------------------------------ epilogue: quads 0,1 -> dV, quads 2,3 -> dK, D/2 columns each ------------------------------
-    mbar_wait(acc_full, 0);
-    tc_fence_after();
-    const int which = q4 >> 1, colhalf = q4 & 1;
-    const uint32_t tAcc = tmem_base + lane_off + 256 + which * D + colhalf * (D / 2);
-    float *dst = (which == 0 ? p.dV : p.dK) + kv_off + (int64_t)key * D + colhalf * (D / 2);
-#pragma unroll
-    for (int cc = 0; cc < D / 64; ++cc) {
-      uint32_t a[32];
-      tmem_ld32(tAcc + cc * 32, a);
-      tmem_wait_ld();
-      if (key < p.Nk) {
-        float4 *d4 = reinterpret_cast<float4 *>(dst + cc * 32);
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          d4[e] = make_float4(__uint_as_float(a[4 * e]), __uint_as_float(a[4 * e + 1]),
-                              __uint_as_float(a[4 * e + 2]), __uint_as_float(a[4 * e + 3]));
-      }
-    }
-  } else {
-    setmaxnreg_dec<64>();
-    if (warp == kDkdv16LoadWarp) {
-      if (elect_one()) {
-        prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
-        mbar_arrive_expect_tx(res_full, 2 * Cfg::kTile);
-        tma_load_tile<D>(sK, &tmK, res_full, key0, h, b);
-        tma_load_tile<D>(sV, &tmV, res_full, key0, h, b);
-        for (int i = 0; i < n; ++i) {
-          const int q0 = (i_start + i) * 128;
-          const int qs = i % Cfg::kQSlots, ds = i % Cfg::kDoSlots;
-          mbar_wait(&q_empty[qs], ((i / Cfg::kQSlots) & 1) ^ 1);
-          mbar_arrive_expect_tx(&q_full[qs], Cfg::kTile);
-          tma_load_tile<D>(sQ + qs * Cfg::kTile, &tmQ, &q_full[qs], q0, h, b);
-          mbar_wait(&do_empty[ds], ((i / Cfg::kDoSlots) & 1) ^ 1);
-          mbar_arrive_expect_tx(&do_full[ds], Cfg::kTile);
-          tma_load_tile<D>(sDO + ds * Cfg::kTile, &tmdO, &do_full[ds], q0, h, b);
-        }
-      }
-      __syncwarp();
-    } else if (warp == kDkdv16MmaWarp) {
-      if (elect_one()) {
-        constexpr uint32_t idesc_xy = make_idesc(128, 128, IS_BF16, 0, 0);
-        constexpr uint32_t idesc_acc = make_idesc(128, D, IS_BF16, 0, 1);
-        const uint32_t sK_a = smem_u32(sK), sV_a = smem_u32(sV), sQ_a = smem_u32(sQ), sDO_a = smem_u32(sDO);
-        const uint32_t tX = tmem_base, tY = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + D;
-        auto q_addr = [&](int i) { return sQ_a + (i % Cfg::kQSlots) * Cfg::kTile; };
-        auto do_addr = [&](int i) { return sDO_a + (i % Cfg::kDoSlots) * Cfg::kTile; };
-        // 16-bit operand of k-step kk (16 query rows): half kk >> 2, chunk (kk & 3) >> 1, 8 columns per k-step
-        auto a_col = [](int kk) { return (uint32_t)((kk >> 2) * 64 + ((kk & 3) >> 1) * 32 + (kk & 1) * 8); };
-        auto issue_x = [&](int i) {
-          mbar_wait(&q_full[i % Cfg::kQSlots], (i / Cfg::kQSlots) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk)
-            mma_ss(tX, kmajor_desc(sK_a, kk), kmajor_desc(q_addr(i), kk), idesc_xy, kk > 0);
-          tc_commit(x_full);
-        };
-        auto issue_y = [&](int i) {
-          mbar_wait(&do_full[i % Cfg::kDoSlots], (i / Cfg::kDoSlots) & 1);
-          tc_fence_after();
-#pragma unroll
-          for (int kk = 0; kk < D / 16; ++kk)
-            mma_ss(tY, kmajor_desc(sV_a, kk), kmajor_desc(do_addr(i), kk), idesc_xy, kk > 0);
-          tc_commit(y_full);
-        };
-        mbar_wait(res_full, 0);
-        tc_fence_after();
-        issue_x(0);
-        issue_y(0);
-        for (int i = 0; i < n; ++i) {
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {  // dV += P^T dO_i; part = chunk c of both halves
-            mbar_wait(&p_ready[part], i & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int kk = (q >> 1) * 4 + part * 2 + (q & 1);
-              mma_ts(tdV, tX + a_col(kk), mnmajor_desc(do_addr(i), kk), idesc_acc, (i > 0 || part > 0 || q > 0) ? 1u : 0u);
-            }
-          }
-          tc_commit(&do_empty[i % Cfg::kDoSlots]);
-          if (i + 1 < n) issue_x(i + 1);
-#pragma unroll
-          for (int part = 0; part < 2; ++part) {  // dK += dS^T Q_i
-            mbar_wait(&ds_ready[part], i & 1);
-            tc_fence_after();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int kk = (q >> 1) * 4 + part * 2 + (q & 1);
-              mma_ts(tdK, tY + a_col(kk), mnmajor_desc(q_addr(i), kk), idesc_acc, (i > 0 || part > 0 || q > 0) ? 1u : 0u);
-            }
-          }
-          tc_commit(&q_empty[i % Cfg::kQSlots]);
-          if (i == n - 1) tc_commit(acc_full);
-          if (i + 1 < n) issue_y(i + 1);
-        }
-      }
-      __syncwarp();
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == kDkdv16MmaWarp) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
-}
-
-// ---------------------------------------------------------------------------
 // 3. dQ : CTA owns 2 x 128 query rows.  Warpgroup t owns tile t (one thread per query row, all
 //    128 key columns); the two tiles take turns on ONE S / dP buffer pair:
 //    TMEM: X = S [0,128)   Y = dP [128,256) (dS aliases its first 64 columns)
@@ -865,7 +573,7 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
 
   if (warp < 8) {
     // ======================= element-wise warpgroups =======================
-    setmaxnreg_inc<kBwdRegsWide>();
+    setmaxnreg_inc<216>();
     const int t = warp >> 2;
     const int tid = (warp & 3) * 32 + lane;
     const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
@@ -965,7 +673,7 @@ bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ C
       }
     }
   } else {
-    setmaxnreg_dec<kBwdRegsNarrow>();
+    setmaxnreg_dec<64>();
     if (warp == kLoadWarp) {
       if (elect_one()) {
         prefetch_tensormap(&tmQ); prefetch_tensormap(&tmK); prefetch_tensormap(&tmV); prefetch_tensormap(&tmdO);
@@ -1074,10 +782,7 @@ int configure_bwd() {
     FA_CUDA_CHECK(cudaFuncSetAttribute(bwd_dq_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        DqCfg<D>::kSmemBytes));
     cudaFuncAttributes attr;  // forces the (lazily loaded) kernels into the context
-    FA_CUDA_CHECK(cudaFuncSetAttribute(bwd_dkdv16_kernel<D, IS_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       DkdvCfg<D>::kSmemBytes));
     FA_CUDA_CHECK(cudaFuncGetAttributes(&attr, bwd_dkdv_kernel<D, IS_BF16>));
-    FA_CUDA_CHECK(cudaFuncGetAttributes(&attr, bwd_dkdv16_kernel<D, IS_BF16>));
     FA_CUDA_CHECK(cudaFuncGetAttributes(&attr, bwd_dq_kernel<D, IS_BF16>));
     FA_CUDA_CHECK(cudaFuncGetAttributes(&attr, bwd_delta_kernel<D, IS_BF16>));
     return (int)FA_OK;
@@ -1094,11 +799,7 @@ int launch_bwd_impl(const CUtensorMap *const *maps, const BwdParams &p, int B, c
   q.group = dispatch_group(p.causal != 0, (int64_t)2 * (p.Nq > p.Nk ? p.Nq : p.Nk) * D * 2, q.n_heads);
   if ((p.Nk + 127) / 128 > 65535 || (p.Nq + 255) / 256 > 65535) q.group = 1;  // grid.y limit of the grouped form
   if (p.dK != nullptr) {
-    if (dkdv_warps() == 16)
-      bwd_dkdv16_kernel<D, IS_BF16><<<dispatch_grid(q.group, (p.Nk + 127) / 128, p.H, B), kDkdv16Threads, DkdvCfg<D>::kSmemBytes, stream>>>(
-          *maps[0], *maps[1], *maps[2], *maps[3], q);
-    else
-      bwd_dkdv_kernel<D, IS_BF16><<<dispatch_grid(q.group, (p.Nk + 127) / 128, p.H, B), kBwdThreads, DkdvCfg<D>::kSmemBytes, stream>>>(
+    bwd_dkdv_kernel<D, IS_BF16><<<dispatch_grid(q.group, (p.Nk + 127) / 128, p.H, B), kBwdThreads, DkdvCfg<D>::kSmemBytes, stream>>>(
         *maps[0], *maps[1], *maps[2], *maps[3], q);
     FA_CUDA_CHECK(cudaGetLastError());
     count_launch();

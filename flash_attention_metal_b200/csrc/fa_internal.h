@@ -126,7 +126,6 @@ int launch_bwd_fused(const void *Q, const void *K, const void *V, const void *dO
                      int B, int H, int dtype, void *sems, cudaStream_t stream);
 // FA_BWD_TWO_KERNEL (default) or FA_BWD_FUSED: fa_set_backward_algorithm
 int bwd_mode();
-// element-wise warps of the dK/dV kernel: 8 (default) or 16 (bwd_dkdv16_kernel; fa_debug_set_dkdv_warps)
-int dkdv_warps();
+
 
 }  // namespace fa

@@ -14,25 +14,19 @@ TOL_ABS = 2e-2
 TOL_REL = {oracle.FP16: 2e-3, oracle.BF16: 1e-2}
 
 
-@pytest.fixture(scope="module", params=["fused", "two_kernel", "two_kernel_16_warps"])
+@pytest.fixture(scope="module", params=["fused", "two_kernel"])
 def fa(request):
     """Every test of this file runs on both implementations of the backward: the two-kernel form
     (csrc/bwd_tc.cu, the default) and the fused five-GEMM kernel (csrc/bwd_fused.cu), selected with
-    fa_set_backward_algorithm -- and the two-kernel form once more with the 16-warp dK/dV kernel."""
+    fa_set_backward_algorithm."""
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import flash_attention_metal_b200 as fa
 
-    import ctypes
-
-    setw = fa.lib().fa_debug_set_dkdv_warps  # 16: the dK/dV kernel with sixteen element-wise warps (bwd_dkdv16_kernel)
-    setw.argtypes = [ctypes.c_int]
     fa.set_backward_algorithm(fa.BWD_FUSED if request.param == "fused" else fa.BWD_TWO_KERNEL)
-    setw(16 if request.param.endswith("16_warps") else 8)
     yield fa
     fa.set_backward_algorithm(fa.BWD_TWO_KERNEL)
-    setw(8)
 
 
 def dev(x):
