@@ -14,8 +14,12 @@
  *     (kernels.metal:622, 932); L is contiguous [B, H, N] (kernels.metal:623).
  *   - `scale` multiplies the dot product (kernels.metal:40, 146, 563, 763).
  *   - causal: key j is excluded for query i when j > i (kernels.metal:748).
- *   - all data pointers are DEVICE pointers, caller-owned, 16-byte aligned; the
- *     library allocates nothing and keeps no state between calls.
+ *   - all data pointers are DEVICE pointers, caller-owned, 16-byte aligned.  The
+ *     single-GPU entry points allocate nothing (scratch comes from the caller's
+ *     workspace) and keep no state between calls beyond a per-thread cache of
+ *     encoded TMA descriptors and the process-wide backward-algorithm setting;
+ *     the objects that own device memory say so (fa_ring_t: its peer window,
+ *     fa_mgpu_t: streams, scratch and windows, fa_host_*: a scratch pool per device).
  *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL =
  *     the default stream) and return 0 on success or a negative FA_ERR_* code;
  *     fa_last_error() gives the message (thread-local).  The reference exits the
