@@ -210,3 +210,52 @@ def test_ring_api_argument_errors_without_gpu(fa):
     assert L.fa_ring_workspace_bytes_backward(1024, 128, 4, fa.BF16) > small
     # the backward workspace covers the fused kernel's ordering counters and delta
     assert fa.workspace_bytes_backward(1000, 128, 2, 3) >= 2 * 3 * 1000 * 4 + 2 * 3 * 8 * 4
+
+
+def fold_like_the_kernel_epilogue(mode, o_part, l_part, o_acc, l_acc):
+    """What fwd_tc_kernel's epilogue does with a launch's partial (csrc/fwd_tc.cu store_rows): returns
+    (final O or None, final L or None, new o_acc, new l_acc)."""
+    if mode == 0:                                   # the only partial: straight to O and L
+        return o_part, l_part, o_acc, l_acc
+    if mode == 1:                                   # first: the running pair starts
+        return None, None, o_part.copy(), l_part.copy()
+    o_new, l_new = merge(o_acc, l_acc, o_part, l_part)
+    if mode == 2:                                   # middle: folded into the running pair
+        return None, None, o_new, l_new
+    return o_new, l_new, o_acc, l_acc               # last: folded and written out
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 5, 8])
+@pytest.mark.parametrize("causal", [False, True])
+def test_schedule_with_fused_merge_modes_reproduces_full_attention(fa, world, causal):
+    """The forward exactly as the ring driver runs it since round 2: one launch per step whose epilogue folds the
+    partial into a running (O, L) pair according to fa_ring_merge_plan, per zig-zag half -- replayed with the
+    oracle as the per-block kernel.  The running pair starts as NaN, as uninitialised workspace might: a mode
+    that reads it before a 'first' wrote it poisons the result."""
+    n_local = 16
+    n = world * n_local
+    q, k, v = (oracle.init_random(n * D, 70 + i).reshape(n, D) for i in range(3))
+    want, want_l = oracle.forward(q, k, v, SCALE, causal)
+    for rank in range(world):
+        rows = local_rows(fa, rank, world, n_local, causal)
+        ql = q[rows]
+        o_acc = np.full((n_local, D), np.nan)
+        l_acc = np.full(n_local, np.nan)
+        o_out = np.full((n_local, D), np.nan)
+        l_out = np.full(n_local, np.nan)
+        for step in range(world):
+            src, q_off, q_rows, k_off, k_rows, bc = fa.ring_plan(rank, world, step, n_local, causal)
+            lo, hi, half = fa.ring_merge_plan(rank, world, step, n_local, causal)
+            srows = local_rows(fa, src, world, n_local, causal)
+            o, l = block_attention(ql[q_off:q_off + q_rows], k[srows][k_off:k_off + k_rows], v[srows][k_off:k_off + k_rows], bool(bc))
+            for r0, r1, mode in ((0, min(half, q_rows), lo), (min(half, q_rows), q_rows, hi)):
+                if r1 <= r0:
+                    continue
+                sl = slice(q_off + r0, q_off + r1)
+                fo, fl, o_acc[sl], l_acc[sl] = fold_like_the_kernel_epilogue(mode, o[r0:r1].astype(np.float64), l[r0:r1].astype(np.float64),
+                                                                           o_acc[sl], l_acc[sl])
+                if fo is not None:
+                    assert np.isnan(o_out[sl]).all()   # every row is written out exactly once
+                    o_out[sl], l_out[sl] = fo, fl
+        assert np.abs(o_out - want[rows]).max() < 2e-6
+        assert np.abs(l_out - want_l[rows]).max() < 2e-6
